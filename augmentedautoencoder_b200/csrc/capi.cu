@@ -1,0 +1,773 @@
+// C ABI of libaae_b200.so (declared in include/aae_b200.h): handle lifetime, weight upload, and the
+// launch sequences that replace the reference's `session.run(...)` calls.
+#include <math.h>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "match.cuh"
+#include "tc.cuh"
+
+namespace aae {
+
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+struct DevBuf {
+  float* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    if (count == 0) return AAE_OK;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(float));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      set_error("cudaMalloc(%zu floats) failed: %s", count, cudaGetErrorString(e));
+      return e == cudaErrorMemoryAllocation ? AAE_ERR_OOM : AAE_ERR_CUDA;
+    }
+    n = count;
+    return AAE_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct ConvLayer {
+  int in_h, in_w, in_c;     // stored input dims
+  int out_h, out_w, out_c;
+  int ksize, stride, pad_t, pad_l, ups, act;
+  DevBuf w, b;              // HWIO kernel, bias
+  DevBuf out;               // activation [max_batch, out_h, out_w, out_c]
+  size_t w_count() const { return (size_t)ksize * ksize * in_c * out_c; }
+};
+
+void tf_same_pad(int in, int k, int stride, int* before) {
+  const int out = (in + stride - 1) / stride;
+  const int total = std::max((out - 1) * stride + k - in, 0);
+  *before = total / 2;  // TF: pad_before = total // 2, remainder goes after (asymmetric for stride 2)
+}
+
+// Pick a split-K factor so that small-M GEMMs still fill the 148 SMs.
+int choose_splits(int64_t M, int64_t N, int64_t K, size_t partial_cap_floats) {
+  const int64_t tiles = ceil_div(M, 128) * ceil_div(N, 128);
+  const int64_t chunks = ceil_div(K, 16);
+  if (tiles >= 148 || chunks < 8) return 1;
+  int64_t s = std::min<int64_t>(ceil_div(296, tiles), chunks / 4);
+  if (partial_cap_floats > 0) s = std::min<int64_t>(s, (int64_t)(partial_cap_floats / (size_t)(M * N)));
+  return (int)std::max<int64_t>(s, 1);
+}
+
+int run_igemm(IGemmParams p, int mode, DevBuf& partials, float* out, const float* bias, int act, const float* mask,
+              cudaStream_t stream) {
+  const int64_t chunks = ceil_div(p.K, 16);
+  int splits = choose_splits(p.M, p.N, p.K, partials.n);
+  if (splits <= 1) {
+    p.k_per_split = (int)chunks * 16;
+    p.C = out; p.bias = bias; p.act = act; p.relu_mask = mask;
+    return launch_igemm(p, mode, stream);
+  }
+  p.k_per_split = (int)ceil_div(chunks, splits) * 16;
+  splits = (int)ceil_div(p.K, p.k_per_split);
+  p.C = partials.p; p.bias = nullptr; p.act = ACT_NONE; p.relu_mask = nullptr;
+  AAE_TRY(launch_igemm(p, mode, stream));
+  AAE_TRY(launch_splitk_reduce(partials.p, splits, (int64_t)p.M * p.N, p.N, bias, act, out, stream));
+  if (mask) AAE_TRY(launch_mul_mask(out, mask, (int64_t)p.M * p.N, stream));
+  return AAE_OK;
+}
+
+IGemmParams conv_params(const ConvLayer& L, const void* src, int src_u8, int B) {
+  IGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = src; p.src_u8 = src_u8;
+  p.B = B; p.SH = L.in_h; p.SW = L.in_w; p.SC = L.in_c; p.ups = L.ups;
+  p.PH = L.out_h; p.PW = L.out_w;
+  p.KH = p.KW = L.ksize; p.stride = L.stride; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
+  p.Bm = L.w.p; p.N = L.out_c;
+  p.M = B * L.out_h * L.out_w;
+  p.K = L.ksize * L.ksize * L.in_c;
+  return p;
+}
+
+IGemmParams dense_params(const float* src, int B, int in_features, const float* w, int out_features) {
+  IGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = src; p.B = B; p.SH = p.SW = 1; p.SC = in_features;
+  p.PH = p.PW = 1; p.KH = p.KW = 1; p.stride = 1;
+  p.Bm = w; p.N = out_features; p.M = B; p.K = in_features;
+  return p;
+}
+
+int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  AAE_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+  return AAE_OK;
+}
+
+}  // namespace
+}  // namespace aae
+
+using namespace aae;
+
+// ============================================================================ handles
+struct aae_encoder {
+  int device;
+  aae_net_cfg cfg;
+  std::vector<ConvLayer> conv;
+  int flat;                 // features entering the dense layer
+  DevBuf dense_w, dense_b;  // [flat, latent], [latent]
+  DevBuf partials;          // split-K scratch
+  TcEncoder* tc = nullptr;  // tensor-core execution plan (AAE_PREC_TC_SPLIT)
+  int last_batch = 0;
+  bool last_was_tc = false;
+};
+
+struct aae_decoder {
+  int device;
+  aae_net_cfg cfg;
+  int h0, w0, f0;           // spatial size / filters after the dense layer
+  DevBuf dense_w, dense_b;  // [latent, h0*w0*f0]
+  DevBuf dense_out;         // [max_batch, h0, w0, f0]  (post ReLU)
+  std::vector<ConvLayer> conv;  // forward order; conv.back() is the sigmoid output layer
+  DevBuf partials;
+  int last_batch = 0;
+};
+
+struct aae_codebook {
+  int device;
+  int64_t n_rows, row_offset;
+  int latent, num_cyclo, max_batch, precision;
+  DevBuf E;            // [n_rows, latent] fp32
+  DevBuf zq;           // [max_batch, latent]
+  DevBuf partial_s;    // [tiles, max_batch]
+  DevBuf partial_i;    // (int32 stored in a float-sized buffer)
+  DevBuf cos;          // lazily allocated [max_batch, n_rows] for k > 1
+  TcCodebook* tc = nullptr;
+};
+
+struct ParamGrad {
+  float* p; size_t n;   // parameter (owned by encoder/decoder)
+  DevBuf g, m, v;
+};
+
+struct aae_trainer {
+  aae_encoder* enc;
+  aae_decoder* dec;
+  int bootstrap_ratio;
+  float lr, b1, b2, eps;
+  int64_t step = 0;
+  // gradients / Adam state: enc conv kernels+biases, enc dense, dec dense, dec convs (same order as *_set_weights)
+  std::vector<ParamGrad> enc_k, enc_b, dec_k, dec_b;
+  DevBuf dx_out;        // dLoss/d(decoder output) then pre-sigmoid grad  [B, H, W, C]
+  DevBuf grad_a, grad_b;  // ping-pong pre-activation gradients
+  DevBuf dxup;          // full-resolution dgrad scratch (before 2x2 sum pooling)
+  DevBuf wt;            // transposed-weight scratch
+  DevBuf partials;      // split-K / small-N partials
+  DevBuf bias_scratch;  // 256 * max(out_c)
+  DevBuf sample_sums, z, dz, rec;
+};
+
+// ============================================================================ misc
+extern "C" int aae_version(void) { return 100; }
+extern "C" int64_t aae_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" const char* aae_last_error_string(void) { return g_err; }
+
+extern "C" int aae_device_supported(int device) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return prop.major == 10 ? 1 : 0;
+}
+
+static int check_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: this library has no CPU fallback");
+    return AAE_ERR_NO_DEVICE;
+  }
+  AAE_REQUIRE(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+  return AAE_OK;
+}
+
+static int check_cfg(const aae_net_cfg* cfg) {
+  AAE_REQUIRE(cfg != nullptr, "cfg is null");
+  AAE_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= AAE_MAX_LAYERS, "num_layers=%d out of range", cfg->num_layers);
+  AAE_REQUIRE(cfg->in_h > 0 && cfg->in_w > 0 && cfg->in_c > 0 && cfg->latent > 0 && cfg->max_batch > 0, "bad geometry");
+  AAE_REQUIRE(cfg->kernel_size >= 1 && cfg->kernel_size <= 7, "kernel_size=%d unsupported", cfg->kernel_size);
+  AAE_REQUIRE(cfg->latent % 4 == 0, "latent=%d must be a multiple of 4", cfg->latent);
+  for (int i = 0; i < cfg->num_layers; ++i) {
+    AAE_REQUIRE(cfg->strides[i] == 1 || cfg->strides[i] == 2, "stride[%d]=%d unsupported (1 or 2)", i, cfg->strides[i]);
+    AAE_REQUIRE(cfg->filters[i] > 0 && cfg->filters[i] % 4 == 0, "filters[%d]=%d must be a positive multiple of 4", i, cfg->filters[i]);
+  }
+  return AAE_OK;
+}
+
+// ============================================================================ encoder
+extern "C" int aae_encoder_create(int device, const aae_net_cfg* cfg, aae_encoder** out) {
+  AAE_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  AAE_TRY(check_cfg(cfg));
+  AAE_TRY(check_device(device));
+  DeviceGuard g(device);
+  aae_encoder* h = new (std::nothrow) aae_encoder();
+  AAE_REQUIRE(h != nullptr, "host allocation failed");
+  h->device = device;
+  h->cfg = *cfg;
+  int ih = cfg->in_h, iw = cfg->in_w, ic = cfg->in_c;
+  int st = AAE_OK;
+  size_t max_partial = 0;
+  for (int i = 0; i < cfg->num_layers && st == AAE_OK; ++i) {
+    ConvLayer L;
+    L.in_h = ih; L.in_w = iw; L.in_c = ic;
+    L.stride = cfg->strides[i]; L.ksize = cfg->kernel_size; L.ups = 0; L.act = ACT_RELU;
+    L.out_h = (ih + L.stride - 1) / L.stride; L.out_w = (iw + L.stride - 1) / L.stride; L.out_c = cfg->filters[i];
+    tf_same_pad(ih, L.ksize, L.stride, &L.pad_t);
+    tf_same_pad(iw, L.ksize, L.stride, &L.pad_l);
+    h->conv.push_back(L);
+    ConvLayer& R = h->conv.back();
+    if ((st = R.w.alloc(R.w_count())) != AAE_OK) break;
+    if ((st = R.b.alloc(R.out_c)) != AAE_OK) break;
+    if ((st = R.out.alloc((size_t)cfg->max_batch * R.out_h * R.out_w * R.out_c)) != AAE_OK) break;
+    cudaMemset(R.w.p, 0, R.w.n * sizeof(float));
+    cudaMemset(R.b.p, 0, R.b.n * sizeof(float));
+    ih = R.out_h; iw = R.out_w; ic = R.out_c;
+  }
+  if (st == AAE_OK) {
+    h->flat = ih * iw * ic;
+    st = h->dense_w.alloc((size_t)h->flat * cfg->latent);
+    if (st == AAE_OK) st = h->dense_b.alloc(cfg->latent);
+    if (st == AAE_OK) {
+      cudaMemset(h->dense_w.p, 0, h->dense_w.n * sizeof(float));
+      cudaMemset(h->dense_b.p, 0, h->dense_b.n * sizeof(float));
+      // split-K scratch for the skinny dense layer: up to 296 splits of [max_batch, latent]
+      max_partial = (size_t)320 * std::max(cfg->max_batch, 128) * cfg->latent;
+      st = h->partials.alloc(max_partial);
+    }
+  }
+  if (st == AAE_OK && cfg->precision == AAE_PREC_TC_SPLIT) st = tc_encoder_create(device, cfg, &h->tc);
+  if (st != AAE_OK) { aae_encoder_destroy(h); return st; }
+  *out = h;
+  return AAE_OK;
+}
+
+extern "C" int aae_encoder_destroy(aae_encoder* h) {
+  if (!h) return AAE_OK;
+  DeviceGuard g(h->device);
+  for (auto& L : h->conv) { L.w.release(); L.b.release(); L.out.release(); }
+  h->dense_w.release(); h->dense_b.release(); h->partials.release();
+  if (h->tc) tc_encoder_destroy(h->tc);
+  delete h;
+  return AAE_OK;
+}
+
+extern "C" int aae_encoder_set_weights(aae_encoder* h, int layer, const float* kernel_any, const float* bias_any, void* stream) {
+  AAE_REQUIRE(h != nullptr, "encoder handle is null");
+  AAE_REQUIRE(layer >= 0 && layer <= (int)h->conv.size(), "layer %d out of range", layer);
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  DevBuf& w = layer < (int)h->conv.size() ? h->conv[layer].w : h->dense_w;
+  DevBuf& b = layer < (int)h->conv.size() ? h->conv[layer].b : h->dense_b;
+  if (kernel_any) AAE_TRY(copy_any(w.p, kernel_any, w.n * sizeof(float), s));
+  if (bias_any) AAE_TRY(copy_any(b.p, bias_any, b.n * sizeof(float), s));
+  if (h->tc && kernel_any) AAE_TRY(tc_encoder_pack_weights(h->tc, layer, w.p, s));
+  AAE_CUDA_OK(cudaStreamSynchronize(s));  // host source buffers may be freed by the caller on return
+  return AAE_OK;
+}
+
+extern "C" int aae_encoder_get_weights(aae_encoder* h, int layer, float* kernel_any, float* bias_any, void* stream) {
+  AAE_REQUIRE(h != nullptr, "encoder handle is null");
+  AAE_REQUIRE(layer >= 0 && layer <= (int)h->conv.size(), "layer %d out of range", layer);
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  DevBuf& w = layer < (int)h->conv.size() ? h->conv[layer].w : h->dense_w;
+  DevBuf& b = layer < (int)h->conv.size() ? h->conv[layer].b : h->dense_b;
+  if (kernel_any) AAE_TRY(copy_any(kernel_any, w.p, w.n * sizeof(float), s));
+  if (bias_any) AAE_TRY(copy_any(bias_any, b.p, b.n * sizeof(float), s));
+  AAE_CUDA_OK(cudaStreamSynchronize(s));
+  return AAE_OK;
+}
+
+static int encoder_forward_simt(aae_encoder* h, const void* crops, int src_u8, int B, float* z_out, cudaStream_t s) {
+  const void* src = crops;
+  int u8 = src_u8;
+  for (auto& L : h->conv) {
+    IGemmParams p = conv_params(L, src, u8, B);
+    AAE_TRY(run_igemm(p, GATHER_FWD, h->partials, L.out.p, L.b.p, L.act, nullptr, s));
+    src = L.out.p;
+    u8 = 0;
+  }
+  IGemmParams p = dense_params((const float*)src, B, h->flat, h->dense_w.p, h->cfg.latent);
+  AAE_TRY(run_igemm(p, GATHER_FWD, h->partials, z_out, h->dense_b.p, ACT_NONE, nullptr, s));
+  return AAE_OK;
+}
+
+static int encoder_forward(aae_encoder* h, const void* crops, int src_u8, int B, float* z_out, void* stream) {
+  AAE_REQUIRE(h != nullptr, "encoder handle is null");
+  AAE_REQUIRE(crops != nullptr && z_out != nullptr, "null tensor pointer");
+  AAE_REQUIRE(B >= 1 && B <= h->cfg.max_batch, "batch %d outside [1, max_batch=%d]", B, h->cfg.max_batch);
+  DeviceGuard g(h->device);
+  h->last_batch = B;
+  if (h->tc) {
+    h->last_was_tc = true;
+    return tc_encoder_forward(h->tc, crops, src_u8, B, h->conv[0].w.p, h->conv[0].b.p, h->dense_b.p, z_out, (cudaStream_t)stream);
+  }
+  h->last_was_tc = false;
+  return encoder_forward_simt(h, crops, src_u8, B, z_out, (cudaStream_t)stream);
+}
+
+extern "C" int aae_encoder_forward_u8(aae_encoder* h, const uint8_t* crops_dev, int batch, float* z_out_dev, void* stream) {
+  return encoder_forward(h, crops_dev, 1, batch, z_out_dev, stream);
+}
+extern "C" int aae_encoder_forward_f32(aae_encoder* h, const float* crops_dev, int batch, float* z_out_dev, void* stream) {
+  return encoder_forward(h, crops_dev, 0, batch, z_out_dev, stream);
+}
+
+extern "C" int aae_encoder_activation(aae_encoder* h, int layer, const float** ptr_dev, int64_t* count) {
+  AAE_REQUIRE(h != nullptr && ptr_dev != nullptr && count != nullptr, "null argument");
+  AAE_REQUIRE(layer >= 0 && layer <= (int)h->conv.size(), "layer %d out of range", layer);
+  AAE_REQUIRE(!h->last_was_tc, "fp32 NHWC activations are only kept by the AAE_PREC_FP32_SIMT path");
+  const ConvLayer& L = h->conv[std::min(layer, (int)h->conv.size() - 1)];
+  *ptr_dev = L.out.p;
+  *count = (int64_t)h->last_batch * L.out_h * L.out_w * L.out_c;
+  return AAE_OK;
+}
+
+// ============================================================================ codebook
+extern "C" int aae_codebook_create(int device, const float* embedding_any, int64_t n_rows, int latent, int num_cyclo,
+                                   int64_t row_offset, int max_batch, int precision, aae_codebook** out) {
+  AAE_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  AAE_REQUIRE(embedding_any != nullptr, "embedding is null");
+  AAE_REQUIRE(n_rows >= 1 && n_rows + row_offset < (int64_t)INT32_MAX, "n_rows=%lld (+offset) must fit int32", (long long)n_rows);
+  AAE_REQUIRE(latent >= 4 && latent % 4 == 0 && latent <= 256, "latent=%d must be a multiple of 4 in [4,256]", latent);
+  AAE_REQUIRE(num_cyclo >= 1 && max_batch >= 1 && row_offset >= 0, "bad num_cyclo/max_batch/row_offset");
+  AAE_TRY(check_device(device));
+  DeviceGuard g(device);
+  aae_codebook* h = new (std::nothrow) aae_codebook();
+  AAE_REQUIRE(h != nullptr, "host allocation failed");
+  h->device = device; h->n_rows = n_rows; h->row_offset = row_offset; h->latent = latent;
+  h->num_cyclo = num_cyclo; h->max_batch = max_batch; h->precision = precision;
+  const int tiles = match_simt_tiles(n_rows);
+  int st = h->E.alloc((size_t)n_rows * latent);
+  if (st == AAE_OK) st = h->zq.alloc((size_t)max_batch * latent);
+  if (st == AAE_OK) st = h->partial_s.alloc((size_t)tiles * max_batch);
+  if (st == AAE_OK) st = h->partial_i.alloc((size_t)tiles * max_batch);
+  if (st == AAE_OK) {
+    cudaError_t e = cudaMemcpy(h->E.p, embedding_any, (size_t)n_rows * latent * sizeof(float), cudaMemcpyDefault);
+    if (e != cudaSuccess) { set_error("codebook upload failed: %s", cudaGetErrorString(e)); st = AAE_ERR_CUDA; }
+  }
+  if (st == AAE_OK && precision == AAE_PREC_TC_SPLIT) st = tc_codebook_create(device, h->E.p, n_rows, latent, max_batch, &h->tc);
+  if (st != AAE_OK) { aae_codebook_destroy(h); return st; }
+  *out = h;
+  return AAE_OK;
+}
+
+extern "C" int aae_codebook_destroy(aae_codebook* h) {
+  if (!h) return AAE_OK;
+  DeviceGuard g(h->device);
+  h->E.release(); h->zq.release(); h->partial_s.release(); h->partial_i.release(); h->cos.release();
+  if (h->tc) tc_codebook_destroy(h->tc);
+  delete h;
+  return AAE_OK;
+}
+
+extern "C" int64_t aae_codebook_rows(const aae_codebook* h) { return h ? h->n_rows : -1; }
+
+extern "C" int aae_l2_normalize(const float* z_dev, int batch, int latent, float* zq_out_dev, void* stream) {
+  AAE_REQUIRE(z_dev != nullptr && zq_out_dev != nullptr && batch >= 1 && latent >= 1, "bad arguments");
+  return launch_l2_normalize(z_dev, batch, latent, zq_out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int aae_codebook_cosine(aae_codebook* h, const float* z_dev, int batch, float* cos_out_dev, void* stream) {
+  AAE_REQUIRE(h != nullptr && z_dev != nullptr && cos_out_dev != nullptr, "null argument");
+  AAE_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch %d outside [1, max_batch=%d]", batch, h->max_batch);
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  AAE_TRY(launch_l2_normalize(z_dev, batch, h->latent, h->zq.p, s));
+  return launch_match_simt(h->E.p, h->n_rows, h->latent, h->zq.p, batch, h->row_offset, h->num_cyclo, 0, h->partial_s.p,
+                           (int*)h->partial_i.p, cos_out_dev, nullptr, nullptr, s);
+}
+
+extern "C" int aae_codebook_match(aae_codebook* h, const float* z_dev, int batch, int k, int upright, float* scores_out_dev,
+                                  int32_t* idx_out_dev, void* stream) {
+  AAE_REQUIRE(h != nullptr && z_dev != nullptr && scores_out_dev != nullptr && idx_out_dev != nullptr, "null argument");
+  AAE_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch %d outside [1, max_batch=%d]", batch, h->max_batch);
+  AAE_REQUIRE(k >= 1 && k <= h->n_rows, "k=%d outside [1, n_rows]", k);
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (k == 1) {
+    if (h->tc)
+      return tc_codebook_match(h->tc, h->E.p, z_dev, batch, h->row_offset, h->num_cyclo, upright, scores_out_dev, idx_out_dev, s);
+    AAE_TRY(launch_l2_normalize(z_dev, batch, h->latent, h->zq.p, s));
+    return launch_match_simt(h->E.p, h->n_rows, h->latent, h->zq.p, batch, h->row_offset, h->num_cyclo, upright, h->partial_s.p,
+                             (int*)h->partial_i.p, nullptr, scores_out_dev, idx_out_dev, s);
+  }
+  // k > 1 (Codebook.nearest_rotation(top_n>1), codebook.py:69-71): exact cosine rows, then k selection passes
+  if (h->cos.n < (size_t)h->max_batch * h->n_rows) AAE_TRY(h->cos.alloc((size_t)h->max_batch * h->n_rows));
+  AAE_TRY(launch_l2_normalize(z_dev, batch, h->latent, h->zq.p, s));
+  AAE_TRY(launch_match_simt(h->E.p, h->n_rows, h->latent, h->zq.p, batch, h->row_offset, h->num_cyclo, 0, h->partial_s.p,
+                            (int*)h->partial_i.p, h->cos.p, nullptr, nullptr, s));
+  return launch_topk_from_cos(h->cos.p, h->n_rows, batch, h->row_offset, h->num_cyclo, upright, k, scores_out_dev, idx_out_dev, s);
+}
+
+extern "C" int aae_topk_merge(const float* scores_dev, const int32_t* idx_dev, int n_shards, int batch, int k,
+                              float* scores_out_dev, int32_t* idx_out_dev, void* stream) {
+  AAE_REQUIRE(scores_dev && idx_dev && scores_out_dev && idx_out_dev, "null argument");
+  AAE_REQUIRE(batch >= 1 && k >= 1, "bad batch/k");
+  return launch_topk_merge(scores_dev, idx_dev, n_shards, batch, k, scores_out_dev, idx_out_dev, (cudaStream_t)stream);
+}
+
+// ============================================================================ decoder
+extern "C" int aae_decoder_create(int device, const aae_net_cfg* cfg, aae_decoder** out) {
+  AAE_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  AAE_TRY(check_cfg(cfg));
+  AAE_TRY(check_device(device));
+  DeviceGuard g(device);
+  aae_decoder* h = new (std::nothrow) aae_decoder();
+  AAE_REQUIRE(h != nullptr, "host allocation failed");
+  h->device = device;
+  h->cfg = *cfg;
+  const int L = cfg->num_layers;
+  // decoder.py:41 layer_dimensions with reversed strides; filters reversed (ae_factory.py:62-64)
+  std::vector<int> nf(L), st(L), dims(L);
+  for (int i = 0; i < L; ++i) { nf[i] = cfg->filters[L - 1 - i]; st[i] = cfg->strides[L - 1 - i]; }
+  for (int i = 0; i < L; ++i) {
+    int prod = 1;
+    for (int j = i; j < L; ++j) prod *= st[j];
+    dims[i] = cfg->in_h / prod;
+  }
+  int status = AAE_OK;
+  for (int i = 0; i < L; ++i)
+    if (st[i] != 2) { set_error("decoder: only stride-2 (x2 nearest-neighbour) stages are supported"); status = AAE_ERR_UNSUPPORTED; }
+  if (cfg->in_h != cfg->in_w) { set_error("decoder: square crops only"); status = AAE_ERR_UNSUPPORTED; }
+  if (status == AAE_OK) {
+    h->h0 = h->w0 = dims[0]; h->f0 = nf[0];
+    const size_t dense_out = (size_t)h->h0 * h->w0 * h->f0;
+    status = h->dense_w.alloc((size_t)cfg->latent * dense_out);
+    if (status == AAE_OK) status = h->dense_b.alloc(dense_out);
+    if (status == AAE_OK) status = h->dense_out.alloc((size_t)cfg->max_batch * dense_out);
+    if (status == AAE_OK) { cudaMemset(h->dense_w.p, 0, h->dense_w.n * 4); cudaMemset(h->dense_b.p, 0, h->dense_b.n * 4); }
+  }
+  int ih = dims[0], ic = nf[0];
+  for (int i = 1; i <= L && status == AAE_OK; ++i) {
+    ConvLayer C;
+    C.in_h = C.in_w = ih; C.in_c = ic; C.ups = 1; C.stride = 1; C.ksize = cfg->kernel_size;
+    C.out_h = C.out_w = ih * 2;
+    C.out_c = i < L ? nf[i] : cfg->in_c;
+    C.act = i < L ? ACT_RELU : ACT_SIGMOID;
+    tf_same_pad(C.out_h, C.ksize, 1, &C.pad_t);
+    C.pad_l = C.pad_t;
+    h->conv.push_back(C);
+    ConvLayer& R = h->conv.back();
+    if ((status = R.w.alloc(R.w_count())) != AAE_OK) break;
+    if ((status = R.b.alloc(R.out_c)) != AAE_OK) break;
+    if ((status = R.out.alloc((size_t)cfg->max_batch * R.out_h * R.out_w * R.out_c)) != AAE_OK) break;
+    cudaMemset(R.w.p, 0, R.w.n * 4); cudaMemset(R.b.p, 0, R.b.n * 4);
+    ih = R.out_h; ic = R.out_c;
+  }
+  if (status == AAE_OK) status = h->partials.alloc((size_t)4 << 20);
+  if (status != AAE_OK) { aae_decoder_destroy(h); return status; }
+  *out = h;
+  return AAE_OK;
+}
+
+extern "C" int aae_decoder_destroy(aae_decoder* h) {
+  if (!h) return AAE_OK;
+  DeviceGuard g(h->device);
+  h->dense_w.release(); h->dense_b.release(); h->dense_out.release(); h->partials.release();
+  for (auto& L : h->conv) { L.w.release(); L.b.release(); L.out.release(); }
+  delete h;
+  return AAE_OK;
+}
+
+extern "C" int aae_decoder_set_weights(aae_decoder* h, int layer, const float* kernel_any, const float* bias_any, void* stream) {
+  AAE_REQUIRE(h != nullptr, "decoder handle is null");
+  AAE_REQUIRE(layer >= 0 && layer <= (int)h->conv.size(), "layer %d out of range", layer);
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  DevBuf& w = layer == 0 ? h->dense_w : h->conv[layer - 1].w;
+  DevBuf& b = layer == 0 ? h->dense_b : h->conv[layer - 1].b;
+  if (kernel_any) AAE_TRY(copy_any(w.p, kernel_any, w.n * sizeof(float), s));
+  if (bias_any) AAE_TRY(copy_any(b.p, bias_any, b.n * sizeof(float), s));
+  AAE_CUDA_OK(cudaStreamSynchronize(s));
+  return AAE_OK;
+}
+
+extern "C" int aae_decoder_get_weights(aae_decoder* h, int layer, float* kernel_any, float* bias_any, void* stream) {
+  AAE_REQUIRE(h != nullptr, "decoder handle is null");
+  AAE_REQUIRE(layer >= 0 && layer <= (int)h->conv.size(), "layer %d out of range", layer);
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  DevBuf& w = layer == 0 ? h->dense_w : h->conv[layer - 1].w;
+  DevBuf& b = layer == 0 ? h->dense_b : h->conv[layer - 1].b;
+  if (kernel_any) AAE_TRY(copy_any(kernel_any, w.p, w.n * sizeof(float), s));
+  if (bias_any) AAE_TRY(copy_any(bias_any, b.p, b.n * sizeof(float), s));
+  AAE_CUDA_OK(cudaStreamSynchronize(s));
+  return AAE_OK;
+}
+
+static int decoder_forward_impl(aae_decoder* h, const float* z, int B, float* x_out, cudaStream_t s) {
+  const int dense_out = h->h0 * h->w0 * h->f0;
+  IGemmParams p = dense_params(z, B, h->cfg.latent, h->dense_w.p, dense_out);
+  AAE_TRY(run_igemm(p, GATHER_FWD, h->partials, h->dense_out.p, h->dense_b.p, ACT_RELU, nullptr, s));
+  const float* src = h->dense_out.p;
+  for (size_t i = 0; i < h->conv.size(); ++i) {
+    ConvLayer& L = h->conv[i];
+    IGemmParams q = conv_params(L, src, 0, B);
+    float* dst = (i + 1 == h->conv.size() && x_out) ? x_out : L.out.p;
+    if (L.out_c % 4 != 0) {
+      q.C = dst; q.bias = L.b.p; q.act = L.act;
+      AAE_TRY(launch_conv_small_n(q, s));
+    } else {
+      AAE_TRY(run_igemm(q, GATHER_FWD, h->partials, dst, L.b.p, L.act, nullptr, s));
+    }
+    src = dst;
+  }
+  return AAE_OK;
+}
+
+extern "C" int aae_decoder_forward(aae_decoder* h, const float* z_dev, int batch, float* x_out_dev, void* stream) {
+  AAE_REQUIRE(h != nullptr && z_dev != nullptr && x_out_dev != nullptr, "null argument");
+  AAE_REQUIRE(batch >= 1 && batch <= h->cfg.max_batch, "batch %d outside [1, max_batch=%d]", batch, h->cfg.max_batch);
+  DeviceGuard g(h->device);
+  h->last_batch = batch;
+  return decoder_forward_impl(h, z_dev, batch, x_out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int aae_bootstrap_l2_loss(const float* x_dev, const float* target_dev, int batch, int numel_per_sample,
+                                     int bootstrap_ratio, float* loss_out_dev, float* grad_out_dev, void* stream) {
+  AAE_REQUIRE(x_dev && target_dev && loss_out_dev, "null argument");
+  AAE_REQUIRE(batch >= 1 && numel_per_sample >= 1 && bootstrap_ratio >= 1, "bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* sums = nullptr;
+  AAE_CUDA_OK(cudaMallocAsync(&sums, (size_t)batch * sizeof(float), s));
+  const int k = bootstrap_ratio > 1 ? numel_per_sample / bootstrap_ratio : numel_per_sample;
+  int st = launch_bootstrap_l2(x_dev, target_dev, batch, numel_per_sample, k, sums, loss_out_dev, grad_out_dev, s);
+  cudaFreeAsync(sums, s);
+  return st;
+}
+
+// ============================================================================ trainer
+static int make_pg(std::vector<ParamGrad>& v, DevBuf& param) {
+  v.emplace_back();
+  ParamGrad& g = v.back();
+  g.p = param.p; g.n = param.n;
+  AAE_TRY(g.g.alloc(param.n));
+  AAE_TRY(g.m.alloc(param.n));
+  AAE_TRY(g.v.alloc(param.n));
+  cudaMemset(g.g.p, 0, param.n * 4); cudaMemset(g.m.p, 0, param.n * 4); cudaMemset(g.v.p, 0, param.n * 4);
+  return AAE_OK;
+}
+
+extern "C" int aae_trainer_create(aae_encoder* enc, aae_decoder* dec, int bootstrap_ratio, float learning_rate, float beta1,
+                                  float beta2, float epsilon, aae_trainer** out) {
+  AAE_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  AAE_REQUIRE(enc && dec, "null handle");
+  AAE_REQUIRE(enc->device == dec->device, "encoder and decoder live on different devices");
+  AAE_REQUIRE(enc->tc == nullptr, "training runs on the AAE_PREC_FP32_SIMT encoder path");
+  AAE_REQUIRE(enc->cfg.max_batch == dec->cfg.max_batch && enc->cfg.in_h == dec->cfg.in_h, "encoder/decoder geometry mismatch");
+  DeviceGuard g(enc->device);
+  aae_trainer* h = new (std::nothrow) aae_trainer();
+  AAE_REQUIRE(h != nullptr, "host allocation failed");
+  h->enc = enc; h->dec = dec; h->bootstrap_ratio = bootstrap_ratio;
+  h->lr = learning_rate; h->b1 = beta1; h->b2 = beta2; h->eps = epsilon;
+  int st = AAE_OK;
+  for (auto& L : enc->conv) { if (st == AAE_OK) st = make_pg(h->enc_k, L.w); if (st == AAE_OK) st = make_pg(h->enc_b, L.b); }
+  if (st == AAE_OK) st = make_pg(h->enc_k, enc->dense_w);
+  if (st == AAE_OK) st = make_pg(h->enc_b, enc->dense_b);
+  if (st == AAE_OK) st = make_pg(h->dec_k, dec->dense_w);
+  if (st == AAE_OK) st = make_pg(h->dec_b, dec->dense_b);
+  for (auto& L : dec->conv) { if (st == AAE_OK) st = make_pg(h->dec_k, L.w); if (st == AAE_OK) st = make_pg(h->dec_b, L.b); }
+  const size_t B = enc->cfg.max_batch;
+  size_t max_act = 0, max_up = 0, max_w = std::max(enc->dense_w.n, dec->dense_w.n), max_c = 0;
+  for (auto& L : enc->conv) { max_act = std::max(max_act, L.out.n); max_w = std::max(max_w, L.w.n); max_c = std::max<size_t>(max_c, L.out_c); }
+  for (auto& L : dec->conv) {
+    max_act = std::max(max_act, L.out.n);
+    max_up = std::max(max_up, B * L.out_h * L.out_w * L.in_c);
+    max_w = std::max(max_w, L.w.n);
+    max_c = std::max<size_t>(max_c, L.out_c);
+  }
+  max_act = std::max(max_act, dec->dense_out.n);
+  max_c = std::max<size_t>(max_c, dec->dense_b.n);
+  const size_t out_elems = B * enc->cfg.in_h * enc->cfg.in_w * enc->cfg.in_c;
+  if (st == AAE_OK) st = h->dx_out.alloc(out_elems);
+  if (st == AAE_OK) st = h->rec.alloc(out_elems);
+  if (st == AAE_OK) st = h->grad_a.alloc(max_act);
+  if (st == AAE_OK) st = h->grad_b.alloc(max_act);
+  if (st == AAE_OK) st = h->dxup.alloc(max_up);
+  if (st == AAE_OK) st = h->wt.alloc(max_w);
+  if (st == AAE_OK) st = h->partials.alloc((size_t)48 << 20);
+  if (st == AAE_OK) st = h->bias_scratch.alloc(256 * max_c);
+  if (st == AAE_OK) st = h->sample_sums.alloc(B);
+  if (st == AAE_OK) st = h->z.alloc(B * enc->cfg.latent);
+  if (st == AAE_OK) st = h->dz.alloc(B * enc->cfg.latent);
+  if (st != AAE_OK) { aae_trainer_destroy(h); return st; }
+  *out = h;
+  return AAE_OK;
+}
+
+extern "C" int aae_trainer_destroy(aae_trainer* h) {
+  if (!h) return AAE_OK;
+  DeviceGuard g(h->enc->device);
+  for (auto* v : {&h->enc_k, &h->enc_b, &h->dec_k, &h->dec_b})
+    for (auto& pg : *v) { pg.g.release(); pg.m.release(); pg.v.release(); }
+  h->dx_out.release(); h->grad_a.release(); h->grad_b.release(); h->dxup.release(); h->wt.release(); h->partials.release();
+  h->bias_scratch.release(); h->sample_sums.release(); h->z.release(); h->dz.release(); h->rec.release();
+  delete h;
+  return AAE_OK;
+}
+
+extern "C" int64_t aae_trainer_global_step(const aae_trainer* h) { return h ? h->step : -1; }
+
+// wgrad of one conv layer: dW[tap,ci,co] = sum_pix X[pix@tap,ci] dY[pix,co]
+static int conv_wgrad(aae_trainer* h, const ConvLayer& L, const void* src, int B, const float* dy, float* dw, cudaStream_t s) {
+  IGemmParams p = conv_params(L, src, 0, B);
+  p.Bm = dy;                       // [pixels, out_c]
+  p.K = B * L.out_h * L.out_w;     // reduction over pixels
+  p.M = L.ksize * L.ksize * L.in_c;
+  if (L.out_c % 4 != 0) {
+    const int chunks = 128;
+    AAE_REQUIRE((size_t)chunks * p.M * L.out_c <= h->partials.n, "partials scratch too small");
+    AAE_TRY(launch_wgrad_small_n(p, chunks, h->partials.p, s));
+    return launch_splitk_reduce(h->partials.p, chunks, (int64_t)p.M * L.out_c, L.out_c, nullptr, ACT_NONE, dw, s);
+  }
+  return run_igemm(p, GATHER_WGRAD, h->partials, dw, nullptr, ACT_NONE, nullptr, s);
+}
+
+// dgrad of one conv layer into `dx` ([B, PH, PW, in_c], PH = logical input height)
+static int conv_dgrad(aae_trainer* h, const ConvLayer& L, int B, const float* dy, float* dx, const float* relu_mask, cudaStream_t s) {
+  const int taps = L.ksize * L.ksize;
+  // Wt[tap][co][ci] = W[tap][ci][co]
+  AAE_TRY(launch_transpose_last2(L.w.p, h->wt.p, taps, L.in_c, L.out_c, s));
+  IGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = dy; p.B = B; p.SH = L.out_h; p.SW = L.out_w; p.SC = L.out_c; p.ups = 0;
+  p.PH = L.in_h << L.ups; p.PW = L.in_w << L.ups;
+  p.KH = p.KW = L.ksize; p.stride = L.stride; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
+  p.Bm = h->wt.p; p.N = L.in_c;
+  p.M = B * p.PH * p.PW;
+  p.K = taps * L.out_c;
+  p.parity_major = (L.stride == 2 && (L.out_c % 16 == 0) && (p.PH % 2 == 0) && (p.PW % 2 == 0) && ((p.M / 4) % 128 == 0)) ? 1 : 0;
+  return run_igemm(p, GATHER_DGRAD, h->partials, dx, nullptr, ACT_NONE, relu_mask, s);
+}
+
+static int trainer_fwd_bwd(aae_trainer* h, const float* x, const float* y, int B, float* loss_out, cudaStream_t s) {
+  aae_encoder* E = h->enc;
+  aae_decoder* D = h->dec;
+  const int H = E->cfg.in_h, W = E->cfg.in_w, C = E->cfg.in_c;
+  const int numel = H * W * C;
+  // ---- forward ----
+  E->last_batch = B; E->last_was_tc = false;
+  AAE_TRY(encoder_forward_simt(E, x, 0, B, h->z.p, s));
+  D->last_batch = B;
+  AAE_TRY(decoder_forward_impl(D, h->z.p, B, h->rec.p, s));
+  const int k = h->bootstrap_ratio > 1 ? numel / h->bootstrap_ratio : numel;
+  AAE_TRY(launch_bootstrap_l2(h->rec.p, y, B, numel, k, h->sample_sums.p, loss_out, h->dx_out.p, s));
+  // ---- decoder backward ----
+  AAE_TRY(launch_sigmoid_grad(h->dx_out.p, h->rec.p, (int64_t)B * numel, s));  // grad wrt pre-sigmoid
+  const float* dy = h->dx_out.p;
+  float* ping = h->grad_a.p;
+  float* pong = h->grad_b.p;
+  for (int i = (int)D->conv.size() - 1; i >= 0; --i) {
+    ConvLayer& L = D->conv[i];
+    const float* in_act = i == 0 ? D->dense_out.p : D->conv[i - 1].out.p;
+    const int64_t rows = (int64_t)B * L.out_h * L.out_w;
+    AAE_TRY(launch_bias_grad(dy, rows, L.out_c, h->dec_b[i + 1].g.p, h->bias_scratch.p, s));
+    AAE_TRY(conv_wgrad(h, L, in_act, B, dy, h->dec_k[i + 1].g.p, s));
+    AAE_TRY(conv_dgrad(h, L, B, dy, h->dxup.p, nullptr, s));
+    // backward of the x2 nearest-neighbour resize + ReLU of the producing layer
+    AAE_TRY(launch_sumpool2_mask(h->dxup.p, in_act, ping, B, L.in_h, L.in_w, L.in_c, s));
+    dy = ping;
+    std::swap(ping, pong);
+  }
+  {  // dense_1: dy is [B, h0*w0*f0] (pre-activation gradient)
+    const int dense_out = D->h0 * D->w0 * D->f0, J = D->cfg.latent;
+    AAE_TRY(launch_bias_grad(dy, B, dense_out, h->dec_b[0].g.p, h->bias_scratch.p, s));
+    IGemmParams p = dense_params(h->z.p, B, J, dy, dense_out);  // WGRAD: src = z, "pixels" = B
+    p.K = B; p.M = J;
+    AAE_TRY(run_igemm(p, GATHER_WGRAD, h->partials, h->dec_k[0].g.p, nullptr, ACT_NONE, nullptr, s));
+    AAE_TRY(launch_transpose_last2(D->dense_w.p, h->wt.p, 1, J, dense_out, s));  // [dense_out, J]
+    IGemmParams q = dense_params(dy, B, dense_out, h->wt.p, J);
+    AAE_TRY(run_igemm(q, GATHER_FWD, h->partials, h->dz.p, nullptr, ACT_NONE, nullptr, s));
+  }
+  // ---- encoder backward ----
+  {
+    const int J = E->cfg.latent, nl = (int)E->conv.size();
+    const float* flat = E->conv.back().out.p;
+    AAE_TRY(launch_bias_grad(h->dz.p, B, J, h->enc_b[nl].g.p, h->bias_scratch.p, s));
+    IGemmParams p = dense_params(flat, B, E->flat, h->dz.p, J);  // WGRAD: dW[flat, J]
+    p.K = B; p.M = E->flat;
+    AAE_TRY(run_igemm(p, GATHER_WGRAD, h->partials, h->enc_k[nl].g.p, nullptr, ACT_NONE, nullptr, s));
+    AAE_TRY(launch_transpose_last2(E->dense_w.p, h->wt.p, 1, E->flat, J, s));  // [J, flat]
+    IGemmParams q = dense_params(h->dz.p, B, J, h->wt.p, E->flat);
+    AAE_TRY(run_igemm(q, GATHER_FWD, h->partials, ping, nullptr, ACT_NONE, flat, s));  // masked by ReLU of the last conv
+    dy = ping;
+    std::swap(ping, pong);
+    for (int i = nl - 1; i >= 0; --i) {
+      ConvLayer& L = E->conv[i];
+      const void* in_act = i == 0 ? (const void*)x : (const void*)E->conv[i - 1].out.p;
+      const int64_t rows = (int64_t)B * L.out_h * L.out_w;
+      AAE_TRY(launch_bias_grad(dy, rows, L.out_c, h->enc_b[i].g.p, h->bias_scratch.p, s));
+      AAE_TRY(conv_wgrad(h, L, in_act, B, dy, h->enc_k[i].g.p, s));
+      if (i > 0) {
+        AAE_TRY(conv_dgrad(h, L, B, dy, ping, (const float*)in_act, s));
+        dy = ping;
+        std::swap(ping, pong);
+      }
+    }
+  }
+  return AAE_OK;
+}
+
+static int trainer_check(aae_trainer* h, const float* x, const float* y, int B, float* loss) {
+  AAE_REQUIRE(h && x && y && loss, "null argument");
+  AAE_REQUIRE(B >= 1 && B <= h->enc->cfg.max_batch, "batch %d outside [1, max_batch=%d]", B, h->enc->cfg.max_batch);
+  return AAE_OK;
+}
+
+extern "C" int aae_trainer_forward_backward(aae_trainer* h, const float* x_dev, const float* y_dev, int batch, float* loss_out_dev,
+                                            void* stream) {
+  AAE_TRY(trainer_check(h, x_dev, y_dev, batch, loss_out_dev));
+  DeviceGuard g(h->enc->device);
+  return trainer_fwd_bwd(h, x_dev, y_dev, batch, loss_out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int aae_train_step(aae_trainer* h, const float* x_dev, const float* y_dev, int batch, float* loss_out_dev, void* stream) {
+  AAE_TRY(trainer_check(h, x_dev, y_dev, batch, loss_out_dev));
+  DeviceGuard g(h->enc->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  AAE_TRY(trainer_fwd_bwd(h, x_dev, y_dev, batch, loss_out_dev, s));
+  h->step += 1;
+  const double t = (double)h->step;
+  const float lr_t = (float)((double)h->lr * sqrt(1.0 - pow((double)h->b2, t)) / (1.0 - pow((double)h->b1, t)));
+  for (auto* v : {&h->enc_k, &h->enc_b, &h->dec_k, &h->dec_b})
+    for (auto& pg : *v) AAE_TRY(launch_adam(pg.p, pg.g.p, pg.m.p, pg.v.p, (int64_t)pg.n, lr_t, h->b1, h->b2, h->eps, s));
+  return AAE_OK;
+}
+
+extern "C" int aae_trainer_get_grads(aae_trainer* h, int which, int layer, float* kernel_grad_any, float* bias_grad_any, void* stream) {
+  AAE_REQUIRE(h != nullptr && (which == 0 || which == 1), "bad arguments");
+  std::vector<ParamGrad>& ks = which == 0 ? h->enc_k : h->dec_k;
+  std::vector<ParamGrad>& bs = which == 0 ? h->enc_b : h->dec_b;
+  AAE_REQUIRE(layer >= 0 && layer < (int)ks.size(), "layer %d out of range", layer);
+  DeviceGuard g(h->enc->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (kernel_grad_any) AAE_TRY(copy_any(kernel_grad_any, ks[layer].g.p, ks[layer].n * sizeof(float), s));
+  if (bias_grad_any) AAE_TRY(copy_any(bias_grad_any, bs[layer].g.p, bs[layer].n * sizeof(float), s));
+  AAE_CUDA_OK(cudaStreamSynchronize(s));
+  return AAE_OK;
+}

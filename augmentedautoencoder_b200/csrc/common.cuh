@@ -1,0 +1,112 @@
+// Internal helpers shared by the translation units of libaae_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/aae_b200.h"
+
+namespace aae {
+
+// ---- error plumbing: nothing throws, nothing aborts (SURVEY.md section 8b "Errors") ----------
+void set_error(const char* fmt, ...);
+
+#define AAE_CUDA_OK(expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::aae::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));  \
+      return AAE_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+// after every kernel launch: count it (bench.py reports gpu_launches from this counter) and surface launch errors
+extern std::atomic<long long> g_launches;
+#define AAE_LAUNCH_OK()                          \
+  do {                                           \
+    ::aae::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    AAE_CUDA_OK(cudaGetLastError());             \
+  } while (0)
+
+#define AAE_REQUIRE(cond, ...)              \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::aae::set_error(__VA_ARGS__);        \
+      return AAE_ERR_INVALID_ARG;           \
+    }                                       \
+  } while (0)
+
+#define AAE_TRY(expr)          \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != AAE_OK) return _s; \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- generic implicit-GEMM (SIMT fp32) -----------------------------------------------------
+// C[M,N] = sum_k A[m,k] * Bm[k,n] where A is gathered from an NHWC tensor.
+enum GatherMode : int {
+  GATHER_FWD = 0,    // conv forward:  m = output pixel, k = (tap, ci);   src = p*stride + tap - pad  (>> ups)
+  GATHER_DGRAD = 1,  // conv dgrad:    m = input  pixel, k = (tap, co);   src = (p + pad - tap)/stride if divisible
+  GATHER_WGRAD = 2   // conv wgrad:    m = (tap, ci),    k = pixel;       C[(tap,ci), co] = sum_pix X[pix@tap, ci] * dY[pix, co]
+};
+
+enum Activation : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
+
+struct IGemmParams {
+  // gathered tensor (NHWC): stored dims
+  const void* src;      // float* (or uint8_t* when src_u8)
+  int src_u8;           // 1: src is uint8, value = u8 / 255.f (true divide, via LUT)
+  int B, SH, SW, SC;    // stored batch / height / width / channels of the gathered tensor
+  int ups;              // log2 nearest-neighbour upsample applied to src before the conv (0 or 1)
+  // pixel grid that indexes the gather (FWD: output pixels, DGRAD: input pixels, WGRAD: output pixels)
+  int PH, PW;
+  int KH, KW, stride, pad_t, pad_l;
+  // dense matrix operand
+  const float* Bm;      // FWD/DGRAD: [K, N] row-major (HWIO flattened); WGRAD: dY [pixels, N]
+  int N;                // columns of C
+  // output
+  float* C;             // [M, N] row-major (or split-K partials [splits, M, N])
+  const float* bias;    // [N] or nullptr
+  const float* relu_mask;  // optional [M, N]: C *= (relu_mask > 0)  (fused ReLU backward in DGRAD)
+  int act;
+  int M, K;             // GEMM sizes
+  int k_per_split;      // K range handled per blockIdx.z (multiple of 16); gridDim.z splits
+  int parity_major;     // DGRAD with stride 2: m enumerates pixels parity-class-major (ph,pw,n,i,j)
+};
+
+int launch_igemm(const IGemmParams& p, int mode, cudaStream_t stream);
+// sums split-K partials [splits, M, N] (fixed order) and applies bias + activation
+int launch_splitk_reduce(const float* partials, int splits, int64_t MN, int N, const float* bias, int act, float* out,
+                         cudaStream_t stream);
+
+// ---- small elementwise / layout kernels ----------------------------------------------------
+int launch_transpose_last2(const float* in, float* out, int batch, int rows, int cols, cudaStream_t stream);  // [b,r,c]->[b,c,r]
+int launch_sumpool2_mask(const float* in, const float* mask, float* out, int B, int OH, int OW, int C, cudaStream_t stream);
+int launch_bias_grad(const float* dy, int64_t rows, int N, float* db, float* scratch256N, cudaStream_t stream);  // db[n] = sum_rows dy[row,n]
+int launch_mul_mask(float* dy, const float* y, int64_t n, cudaStream_t stream);              // dy *= (y > 0)
+int launch_sigmoid_grad(float* dx, const float* x, int64_t n, cudaStream_t stream);          // dx *= x (1 - x)
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
+                cudaStream_t stream);
+int launch_conv_small_n(const IGemmParams& p, cudaStream_t stream);
+// p.K = number of pixels, p.Bm = dY [pixels, N<=3]; partial: [chunks, taps*SC*N]
+int launch_wgrad_small_n(const IGemmParams& p, int chunks, float* partial, cudaStream_t stream);
+
+// ---- codebook ------------------------------------------------------------------------------
+int launch_l2_normalize(const float* z, int B, int J, float* out, cudaStream_t stream);
+
+}  // namespace aae

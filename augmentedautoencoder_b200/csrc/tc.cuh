@@ -1,0 +1,22 @@
+// Tensor-core (tcgen05 / TMEM / TMA) execution plans behind AAE_PREC_TC_SPLIT.  Internal to the library.
+#pragma once
+#include "common.cuh"
+
+namespace aae {
+
+struct TcEncoder;
+struct TcCodebook;
+
+int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out);
+void tc_encoder_destroy(TcEncoder* h);
+// (re)pack the fp32 weights of `layer` (device pointer, reference layout) into the split-fp16 operand layout
+int tc_encoder_pack_weights(TcEncoder* h, int layer, const float* w_dev, cudaStream_t s);
+int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const float* w0, const float* b0, const float* dense_b,
+                       float* z_out, cudaStream_t s);
+
+int tc_codebook_create(int device, const float* E_dev, int64_t n_rows, int latent, int max_batch, TcCodebook** out);
+void tc_codebook_destroy(TcCodebook* h);
+int tc_codebook_match(TcCodebook* h, const float* E_dev, const float* z_dev, int B, int64_t row_offset, int num_cyclo, int upright,
+                      float* scores_out, int32_t* idx_out, cudaStream_t s);
+
+}  // namespace aae

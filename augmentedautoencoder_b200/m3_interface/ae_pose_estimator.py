@@ -1,0 +1,130 @@
+"""AePoseEstimator: the m3vision pose-estimation plugin.  Mirrors auto_pose/m3_interface/ae_pose_estimator.py:16-232
+(constructor from a test-config path, attributes read by other tools, ``process`` signature and result type).
+
+B200-first difference: the reference runs one B=1 ``session.run`` per detection (ae_pose_estimator.py:143-170); here all
+detections of a frame that share an object class are cropped, stacked and sent through encoder + fused codebook match
+in ONE batch per class, on the device that owns that class' (encoder, codebook) pair (multi-object routing, F14).
+"""
+import configparser
+import os
+
+import cv2
+import numpy as np
+import torch
+
+from ..ae import factory, utils
+from ..ae.codebook import lift_pose
+from ..ae.session import Session
+from .m3_interfaces import PoseEstimate, PoseEstInterface
+
+
+class AePoseEstimator(PoseEstInterface):
+
+    def __init__(self, test_config_path, devices=None, precision=None):
+        test_args = self.get_params(test_config_path)
+        workspace_path = os.environ.get('AE_WORKSPACE_PATH')
+        if workspace_path is None:
+            raise EnvironmentError('Please define a workspace path: export AE_WORKSPACE_PATH=/path/to/workspace')
+        self._process_requirements = ['color_img', 'camK', 'bboxes']
+        if test_args.getboolean('auto_pose', 'camPose'):
+            self._process_requirements.append('camPose')
+        self._camPose = test_args.getboolean('auto_pose', 'camPose')
+        self._upright = test_args.getboolean('auto_pose', 'upright')
+        self._topk = test_args.getint('auto_pose', 'topk')
+        if self._topk > 1:
+            raise NotImplementedError('topk > 1 not implemented yet')  # reference: print + exit (ae_pose_estimator.py:37-39)
+        self._image_format = {'color_format': test_args.get('auto_pose', 'color_format'),
+                              'color_data_type': eval(test_args.get('auto_pose', 'color_data_type'), {"np": np}),
+                              'depth_data_type': eval(test_args.get('auto_pose', 'depth_data_type'), {"np": np})}
+        self.class_2_encoder = eval(test_args.get('auto_pose', 'class_2_encoder'))
+        self.all_codebooks = {}
+        self.all_train_args = {}
+        self.pad_factors = {}
+        self.patch_sizes = {}
+        n_dev = torch.cuda.device_count()
+        if devices is None:
+            devices = list(range(max(n_dev, 1)))
+        self.sess = Session(device=devices[0])
+        self._sessions = {}
+        for i, (clas_name, experiment) in enumerate(self.class_2_encoder.items()):
+            full_name = experiment.split('/')
+            experiment_name = full_name.pop()
+            experiment_group = full_name.pop() if len(full_name) > 0 else ''
+            log_dir = utils.get_log_dir(workspace_path, experiment_name, experiment_group)
+            ckpt_dir = utils.get_checkpoint_dir(log_dir)
+            train_cfg_file_path = utils.get_train_config_exp_file_path(log_dir, experiment_name)
+            train_args = configparser.ConfigParser(inline_comment_prefixes="#")
+            train_args.read(train_cfg_file_path)
+            self.all_train_args[clas_name] = train_args
+            self.pad_factors[clas_name] = train_args.getfloat('Dataset', 'PAD_FACTOR')
+            self.patch_sizes[clas_name] = (train_args.getint('Dataset', 'W'), train_args.getint('Dataset', 'H'))
+            cb = factory.build_codebook_from_name(experiment_name, experiment_group, return_dataset=False, precision=precision)
+            self.all_codebooks[clas_name] = cb
+            self._sessions[clas_name] = Session(device=devices[i % len(devices)])  # one object per GPU, round robin
+            saver = factory.Saver([cb._encoder, cb])
+            factory.restore_checkpoint(self._sessions[clas_name], saver, ckpt_dir)
+
+    def set_parameter(self, string_name, string_val):
+        pass
+
+    def query_process_requirements(self):
+        return self._process_requirements
+
+    def query_image_format(self):
+        return self._image_format
+
+    def extract_square_patch(self, scene_img, bb_xywh, pad_factor, resize=(128, 128), interpolation=cv2.INTER_NEAREST, black_borders=False):
+        """Square, zero-padded patch around a detection, bbox content centred (ae_pose_estimator.py:106-131; ``process``
+        always uses black_borders=True).  The reference's other branch slices with float indices and cannot run."""
+        x, y, w, h = np.array(bb_xywh).astype(np.int32)
+        size = int(np.maximum(h, w) * pad_factor)
+        scene_crop = np.zeros((size, size, 3), dtype=np.uint8)
+        if not black_borders:
+            raise NotImplementedError("black_borders=False is broken upstream (float slice indices, ae_pose_estimator.py:118-127)")
+        scene_crop[(size - h) // 2:(size - h) // 2 + h, (size - w) // 2:(size - w) // 2 + w] = scene_img[y:y + h, x:x + w].copy()
+        return cv2.resize(scene_crop, resize, interpolation=interpolation)
+
+    def process(self, bboxes, color_img, camK, depth_img=None, camPose=None, rois3ds=[], mm=False):
+        H, W = color_img.shape[:2]
+        jobs = {}  # class -> list of (order, box_xywh, crop)
+        order = 0
+        for box in bboxes:
+            pred_clas = max(box.classes, key=box.classes.get)
+            if pred_clas not in self.class_2_encoder:
+                continue
+            box_xywh = [box.xmin * W, box.ymin * H, (box.xmax - box.xmin) * W, (box.ymax - box.ymin) * H]
+            if np.any(np.array(box_xywh) < 0):
+                continue
+            det_img = self.extract_square_patch(color_img, box_xywh, self.pad_factors[pred_clas], resize=self.patch_sizes[pred_clas],
+                                                interpolation=cv2.INTER_LINEAR, black_borders=True)
+            jobs.setdefault(pred_clas, []).append((order, box_xywh, det_img))
+            order += 1
+        results = [None] * order
+        pending = []
+        for clas, items in jobs.items():  # launch every class' batch first (different GPUs run concurrently) ...
+            cb, sess = self.all_codebooks[clas], self._sessions[clas]
+            crops = np.stack([it[2] for it in items])
+            if crops.dtype != np.uint8:
+                crops = crops.astype(np.float32)
+            with torch.cuda.device(sess.device):
+                xd = torch.from_numpy(crops).to(sess.device, non_blocking=True)
+                _, idx = cb.nearest_idx_device(xd, k=1, upright=self._upright)
+            pending.append((clas, items, idx))
+        for clas, items, idx in pending:     # ... then collect
+            cb, sess = self.all_codebooks[clas], self._sessions[clas]
+            idcs = idx.cpu().numpy().astype(np.int64)[:, 0]
+            train_args = self.all_train_args[clas]
+            K_train = np.array(eval(train_args.get('Dataset', 'K'))).reshape(3, 3)
+            radius = train_args.getfloat('Dataset', 'RADIUS')
+            if cb.embed_obj_bbs_values is None:
+                cb.embed_obj_bbs_values = sess.run(cb.embed_obj_bbs_var)
+            for (o, box_xywh, _), i in zip(items, idcs):
+                Rs, ts = lift_pose(np.array([i]), cb._dataset.viewsphere_for_embedding, cb.embed_obj_bbs_values, box_xywh,
+                                   np.asarray(camK), K_train, radius)
+                H_est = np.eye(4)
+                H_est[:3, :3] = Rs.squeeze()
+                H_est[:3, 3] = ts.squeeze() if mm else ts.squeeze() / 1000.
+                if self._camPose:
+                    H_est = np.dot(camPose, H_est)
+                results[o] = PoseEstimate(name=clas, trafo=H_est)
+        return results

@@ -1,0 +1,159 @@
+/*
+ * aae_b200.h -- C ABI of the B200-native Augmented-Autoencoder hot path.
+ *
+ * The reference (DLR-RM/AugmentedAutoencoder) has no FFI: its device boundary is
+ * `tf.Session.run` on a TensorFlow graph.  Each entry point below
+ * replaces the TensorFlow sub-graph named in its comment; paths are relative to
+ * /root/reference.  The Python classes in augmentedautoencoder_b200/ae/ keep the
+ * reference's class/method surface and bind these symbols through ctypes
+ * (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is a CUDA device pointer on the
+ *     handle's device; pointers named *_any may be host or device (copied with
+ *     cudaMemcpyDefault); `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, a negative aae_status otherwise, never throws
+ *     and never aborts.  aae_last_error_string() describes the last failure on the
+ *     calling thread.
+ *   - handles are re-entrant per (handle, stream): no global mutable state; a handle owns
+ *     its weights, packed operand copies and a private workspace sized by max_batch.
+ *   - tensor layouts follow the reference: activations NHWC float32, conv kernels HWIO,
+ *     dense kernels [in,out], crops BGR uint8 or float32 in [0,1]
+ *     (auto_pose/ae/ae_factory.py:133, auto_pose/ae/encoder.py:43-66).
+ */
+#ifndef AAE_B200_H_
+#define AAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define AAE_API __declspec(dllexport)
+#else
+#define AAE_API __attribute__((visibility("default")))
+#endif
+
+typedef enum {
+  AAE_OK = 0,
+  AAE_ERR_INVALID_ARG = -1,
+  AAE_ERR_CUDA = -2,
+  AAE_ERR_UNSUPPORTED = -3,
+  AAE_ERR_NO_DEVICE = -4,
+  AAE_ERR_OOM = -5
+} aae_status;
+
+/* Arithmetic used for the dense contractions (convs, dense layers, codebook scores).
+ *   AAE_PREC_FP32_SIMT : IEEE fp32 FMA chains on the CUDA cores (exact-order reference path)
+ *   AAE_PREC_TC_SPLIT  : tcgen05 tensor cores, every fp32 operand split into two fp16 terms
+ *                        (hi + 2^-11 lo), three products hi*hi + hi*lo + lo*hi accumulated in
+ *                        fp32 TMEM -- fp32-grade results at tensor-core rate. */
+typedef enum { AAE_PREC_FP32_SIMT = 0, AAE_PREC_TC_SPLIT = 1 } aae_precision;
+
+#define AAE_MAX_LAYERS 8
+
+/* Network geometry: the values `build_encoder` / `build_decoder` read from the training cfg
+ * (auto_pose/ae/ae_factory.py:33-71; template auto_pose/ae/cfg/train_template.cfg:5-9,44-55). */
+typedef struct {
+  int32_t in_h, in_w, in_c;            /* H, W, C of the crop: 128,128,3                          */
+  int32_t num_layers;                  /* len(NUM_FILTER)                                          */
+  int32_t filters[AAE_MAX_LAYERS];     /* NUM_FILTER  (encoder order; the decoder reverses it)     */
+  int32_t strides[AAE_MAX_LAYERS];     /* STRIDES                                                  */
+  int32_t kernel_size;                 /* KERNEL_SIZE_ENCODER / KERNEL_SIZE_DECODER                */
+  int32_t latent;                      /* LATENT_SPACE_SIZE                                        */
+  int32_t max_batch;                   /* workspace is sized for this many crops per call          */
+  int32_t precision;                   /* aae_precision                                            */
+} aae_net_cfg;
+
+typedef struct aae_encoder aae_encoder;
+typedef struct aae_decoder aae_decoder;
+typedef struct aae_codebook aae_codebook;
+typedef struct aae_trainer aae_trainer;
+
+AAE_API int aae_version(void);
+AAE_API const char* aae_last_error_string(void);
+/* 1 if a tcgen05-capable device (compute capability 10.x) is present on `device`, else 0. */
+AAE_API int aae_device_supported(int device);
+/* Total number of CUDA kernels this library has launched in the process (for launch accounting in benchmarks). */
+AAE_API int64_t aae_launch_count(void);
+
+/* ---------------------------------------------------------------- Encoder ------------------
+ * Replaces Encoder.encoder_out + Encoder.z: 4x [conv5x5 / stride 2 / TF-SAME(1,2) + bias + ReLU],
+ * flatten (h,w,c), dense -> latent  (auto_pose/ae/encoder.py:37-68). */
+AAE_API int aae_encoder_create(int device, const aae_net_cfg* cfg, aae_encoder** out);
+AAE_API int aae_encoder_destroy(aae_encoder* h);
+/* layer in [0,num_layers) = conv kernels HWIO [k,k,cin,cout] + bias [cout];
+ * layer == num_layers = dense kernel [flat,latent] + bias [latent]  (variable layouts of
+ * auto_pose/ae/encoder.py:43-50,62-66 as stored in the TF checkpoint). */
+AAE_API int aae_encoder_set_weights(aae_encoder* h, int layer, const float* kernel_any, const float* bias_any, void* stream);
+AAE_API int aae_encoder_get_weights(aae_encoder* h, int layer, float* kernel_any, float* bias_any, void* stream);
+/* crops NHWC uint8 [B,H,W,C]; the x/255. of auto_pose/ae/codebook.py:58-59 is fused (true fp32 divide). */
+AAE_API int aae_encoder_forward_u8(aae_encoder* h, const uint8_t* crops_dev, int batch, float* z_out_dev, void* stream);
+/* crops NHWC float32 in [0,1] (the placeholder of auto_pose/ae/ae_factory.py:133). */
+AAE_API int aae_encoder_forward_f32(aae_encoder* h, const float* crops_dev, int batch, float* z_out_dev, void* stream);
+/* Device pointer + element count of the activation of conv layer `layer` (NHWC fp32) from the last
+ * forward; layer == num_layers gives the flattened encoder_out.  For tests and for the trainer. */
+AAE_API int aae_encoder_activation(aae_encoder* h, int layer, const float** ptr_dev, int64_t* count);
+
+/* ---------------------------------------------------------------- Codebook -----------------
+ * Replaces the Codebook graph: tf.nn.l2_normalize(z,1), matmul(zq, embedding_normalized^T),
+ * argmax (auto_pose/ae/codebook.py:27,50-51) and the host-side np.argmax / strided argmax /
+ * argpartition of Codebook.nearest_rotation (auto_pose/ae/codebook.py:63-71). */
+/* embedding_any: [n_rows, latent] float32, rows already L2-normalised (codebook.py:213-216).
+ * row_offset: global index of row 0 (non-zero when this handle holds one shard of a row-sharded
+ * codebook); reported indices are global. */
+AAE_API int aae_codebook_create(int device, const float* embedding_any, int64_t n_rows, int latent, int num_cyclo,
+                                int64_t row_offset, int max_batch, int precision, aae_codebook** out);
+AAE_API int aae_codebook_destroy(aae_codebook* h);
+/* zq = z * rsqrt(max(sum z^2, 1e-12))  (codebook.py:27). */
+AAE_API int aae_l2_normalize(const float* z_dev, int batch, int latent, float* zq_out_dev, void* stream);
+/* Fused normalise + score + top-k: for every query the k best rows, scores descending, ties broken
+ * towards the LOWEST index (np.argmax semantics, codebook.py:64-68).  upright != 0 restricts the
+ * search to rows with (global index % num_cyclo) == 0 (codebook.py:66).  The [B,N] cosine matrix is
+ * never materialised.  scores_out_dev [B,k] float32, idx_out_dev [B,k] int32 (global row index). */
+AAE_API int aae_codebook_match(aae_codebook* h, const float* z_dev, int batch, int k, int upright,
+                               float* scores_out_dev, int32_t* idx_out_dev, void* stream);
+/* Full cosine matrix [B, n_rows] = `session.run(codebook.cos_similarity)` (codebook.py:50,63). */
+AAE_API int aae_codebook_cosine(aae_codebook* h, const float* z_dev, int batch, float* cos_out_dev, void* stream);
+/* Merge per-shard top-k lists (all-gathered over NCCL by the host): in [n_shards,B,k] -> out [B,k];
+ * equal scores resolve to the lowest global index, so the result is bit-identical to the
+ * unsharded match. */
+AAE_API int aae_topk_merge(const float* scores_dev, const int32_t* idx_dev, int n_shards, int batch, int k,
+                           float* scores_out_dev, int32_t* idx_out_dev, void* stream);
+AAE_API int64_t aae_codebook_rows(const aae_codebook* h);
+
+/* ---------------------------------------------------------------- Decoder + loss -----------
+ * Replaces Decoder.x: dense latent->8*8*512 + ReLU, 3x [NN-resize x2, conv5x5 s1 + ReLU],
+ * NN-resize x2, conv5x5 -> C + sigmoid (auto_pose/ae/decoder.py:36-84). */
+AAE_API int aae_decoder_create(int device, const aae_net_cfg* cfg, aae_decoder** out);
+AAE_API int aae_decoder_destroy(aae_decoder* h);
+/* layer 0 = dense_1 [latent, h0*w0*f0]; layers 1..num_layers = the convs in forward order. */
+AAE_API int aae_decoder_set_weights(aae_decoder* h, int layer, const float* kernel_any, const float* bias_any, void* stream);
+AAE_API int aae_decoder_get_weights(aae_decoder* h, int layer, float* kernel_any, float* bias_any, void* stream);
+AAE_API int aae_decoder_forward(aae_decoder* h, const float* z_dev, int batch, float* x_out_dev, void* stream);
+/* Bootstrapped L2 (LOSS: L2, BOOTSTRAP_RATIO r): per-sample top-k of the flattened squared error,
+ * k = numel/r, mean over the [B,k] survivors (auto_pose/ae/decoder.py:90-101).
+ * grad_out_dev (optional, [B,numel]) receives dLoss/dx. */
+AAE_API int aae_bootstrap_l2_loss(const float* x_dev, const float* target_dev, int batch, int numel_per_sample,
+                                  int bootstrap_ratio, float* loss_out_dev, float* grad_out_dev, void* stream);
+
+/* ---------------------------------------------------------------- Training step ------------
+ * Replaces sess.run(train_op): encoder fwd, decoder fwd, bootstrapped L2, backward, TF-Adam
+ * (auto_pose/ae/ae_train.py:128, auto_pose/ae/ae_factory.py:79-95). */
+AAE_API int aae_trainer_create(aae_encoder* enc, aae_decoder* dec, int bootstrap_ratio, float learning_rate,
+                               float beta1, float beta2, float epsilon, aae_trainer** out);
+AAE_API int aae_trainer_destroy(aae_trainer* h);
+/* x (augmented input) and y (reconstruction target) NHWC float32 [B,H,W,C]; loss_out_dev: 1 float. */
+AAE_API int aae_train_step(aae_trainer* h, const float* x_dev, const float* y_dev, int batch, float* loss_out_dev, void* stream);
+/* forward + backward only (no parameter update); gradients stay in the trainer. */
+AAE_API int aae_trainer_forward_backward(aae_trainer* h, const float* x_dev, const float* y_dev, int batch, float* loss_out_dev, void* stream);
+/* which: 0 = encoder, 1 = decoder; layer as in *_set_weights. */
+AAE_API int aae_trainer_get_grads(aae_trainer* h, int which, int layer, float* kernel_grad_any, float* bias_grad_any, void* stream);
+AAE_API int64_t aae_trainer_global_step(const aae_trainer* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AAE_B200_H_ */
