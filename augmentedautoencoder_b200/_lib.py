@@ -37,6 +37,8 @@ _SIGS = {
     "aae_encoder_forward_u8": (_I, [_P, _P, _I, _P, _P]),
     "aae_encoder_forward_f32": (_I, [_P, _P, _I, _P, _P]),
     "aae_encoder_activation": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_L)]),
+    "aae_encoder_profile": (_I, [_P, _I, _P, _I]),
+    "aae_codebook_profile": (_I, [_P, _I, _P, _I]),
     "aae_codebook_create": (_I, [_I, _P, _L, _I, _I, _L, _I, _I, C.POINTER(_P)]),
     "aae_codebook_destroy": (_I, [_P]),
     "aae_l2_normalize": (_I, [_P, _I, _I, _P, _P]),

@@ -111,6 +111,28 @@ IGemmParams dense_params(const float* src, int B, int in_features, const float* 
   return p;
 }
 
+// Optional per-stage device timing (cudaEvents on the launching stream), read back by bench.py for the roofline lines.
+struct StageTimer {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;   // stage i is bracketed by ev[i], ev[i+1]
+  int used = 0;
+  void mark(cudaStream_t s) {
+    if (!enabled) return;
+    if (used == (int)ev.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; ev.push_back(e); }
+    cudaEventRecord(ev[used++], s);
+  }
+  void reset() { used = 0; }
+  int read(float* ms, int cap) {
+    int n = 0;
+    if (used >= 2) {
+      cudaEventSynchronize(ev[used - 1]);
+      for (int i = 0; i + 1 < used && n < cap; ++i, ++n) cudaEventElapsedTime(&ms[n], ev[i], ev[i + 1]);
+    }
+    return n;
+  }
+  void release() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); used = 0; }
+};
+
 int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   AAE_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
   return AAE_OK;
@@ -132,6 +154,7 @@ struct aae_encoder {
   TcEncoder* tc = nullptr;  // tensor-core execution plan (AAE_PREC_TC_SPLIT)
   int last_batch = 0;
   bool last_was_tc = false;
+  StageTimer timer;
 };
 
 struct aae_decoder {
@@ -155,6 +178,7 @@ struct aae_codebook {
   DevBuf partial_i;    // (int32 stored in a float-sized buffer)
   DevBuf cos;          // lazily allocated [max_batch, n_rows] for k > 1
   TcCodebook* tc = nullptr;
+  StageTimer timer;
 };
 
 struct ParamGrad {
@@ -268,6 +292,7 @@ extern "C" int aae_encoder_destroy(aae_encoder* h) {
   for (auto& L : h->conv) { L.w.release(); L.b.release(); L.out.release(); }
   h->dense_w.release(); h->dense_b.release(); h->partials.release();
   if (h->tc) tc_encoder_destroy(h->tc);
+  h->timer.release();
   delete h;
   return AAE_OK;
 }
@@ -302,14 +327,18 @@ extern "C" int aae_encoder_get_weights(aae_encoder* h, int layer, float* kernel_
 static int encoder_forward_simt(aae_encoder* h, const void* crops, int src_u8, int B, float* z_out, cudaStream_t s) {
   const void* src = crops;
   int u8 = src_u8;
+  h->timer.reset();
+  h->timer.mark(s);
   for (auto& L : h->conv) {
     IGemmParams p = conv_params(L, src, u8, B);
     AAE_TRY(run_igemm(p, GATHER_FWD, h->partials, L.out.p, L.b.p, L.act, nullptr, s));
+    h->timer.mark(s);
     src = L.out.p;
     u8 = 0;
   }
   IGemmParams p = dense_params((const float*)src, B, h->flat, h->dense_w.p, h->cfg.latent);
   AAE_TRY(run_igemm(p, GATHER_FWD, h->partials, z_out, h->dense_b.p, ACT_NONE, nullptr, s));
+  h->timer.mark(s);
   return AAE_OK;
 }
 
@@ -344,7 +373,26 @@ extern "C" int aae_encoder_activation(aae_encoder* h, int layer, const float** p
   return AAE_OK;
 }
 
+extern "C" int aae_encoder_profile(aae_encoder* h, int enable, float* stage_ms_out, int capacity) {
+  AAE_REQUIRE(h != nullptr, "encoder handle is null");
+  DeviceGuard g(h->device);
+  int n = 0;
+  if (stage_ms_out && capacity > 0) n = h->tc ? tc_encoder_read_timer(h->tc, stage_ms_out, capacity) : h->timer.read(stage_ms_out, capacity);
+  h->timer.enabled = enable != 0;
+  if (h->tc) tc_encoder_enable_timer(h->tc, enable != 0);
+  return n;
+}
+
 // ============================================================================ codebook
+extern "C" int aae_codebook_profile(aae_codebook* h, int enable, float* stage_ms_out, int capacity) {
+  AAE_REQUIRE(h != nullptr, "codebook handle is null");
+  DeviceGuard g(h->device);
+  int n = 0;
+  if (stage_ms_out && capacity > 0) n = h->timer.read(stage_ms_out, capacity);
+  h->timer.enabled = enable != 0;
+  return n;
+}
+
 extern "C" int aae_codebook_create(int device, const float* embedding_any, int64_t n_rows, int latent, int num_cyclo,
                                    int64_t row_offset, int max_batch, int precision, aae_codebook** out) {
   AAE_REQUIRE(out != nullptr, "out is null");
@@ -379,6 +427,7 @@ extern "C" int aae_codebook_destroy(aae_codebook* h) {
   DeviceGuard g(h->device);
   h->E.release(); h->zq.release(); h->partial_s.release(); h->partial_i.release(); h->cos.release();
   if (h->tc) tc_codebook_destroy(h->tc);
+  h->timer.release();
   delete h;
   return AAE_OK;
 }
@@ -408,11 +457,20 @@ extern "C" int aae_codebook_match(aae_codebook* h, const float* z_dev, int batch
   DeviceGuard g(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   if (k == 1) {
-    if (h->tc)
-      return tc_codebook_match(h->tc, h->E.p, z_dev, batch, h->row_offset, h->num_cyclo, upright, scores_out_dev, idx_out_dev, s);
+    if (h->tc) {
+      h->timer.reset();
+      h->timer.mark(s);
+      AAE_TRY(tc_codebook_match(h->tc, h->E.p, z_dev, batch, h->row_offset, h->num_cyclo, upright, scores_out_dev, idx_out_dev, s));
+      h->timer.mark(s);
+      return AAE_OK;
+    }
+    h->timer.reset();
+    h->timer.mark(s);
     AAE_TRY(launch_l2_normalize(z_dev, batch, h->latent, h->zq.p, s));
-    return launch_match_simt(h->E.p, h->n_rows, h->latent, h->zq.p, batch, h->row_offset, h->num_cyclo, upright, h->partial_s.p,
-                             (int*)h->partial_i.p, nullptr, scores_out_dev, idx_out_dev, s);
+    AAE_TRY(launch_match_simt(h->E.p, h->n_rows, h->latent, h->zq.p, batch, h->row_offset, h->num_cyclo, upright, h->partial_s.p,
+                              (int*)h->partial_i.p, nullptr, scores_out_dev, idx_out_dev, s));
+    h->timer.mark(s);
+    return AAE_OK;
   }
   // k > 1 (Codebook.nearest_rotation(top_n>1), codebook.py:69-71): exact cosine rows, then k selection passes
   if (h->cos.n < (size_t)h->max_batch * h->n_rows) AAE_TRY(h->cos.alloc((size_t)h->max_batch * h->n_rows));

@@ -14,6 +14,9 @@ int tc_encoder_pack_weights(TcEncoder* h, int layer, const float* w_dev, cudaStr
 int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const float* w0, const float* b0, const float* dense_b,
                        float* z_out, cudaStream_t s);
 
+void tc_encoder_enable_timer(TcEncoder* h, bool on);
+int tc_encoder_read_timer(TcEncoder* h, float* ms, int cap);
+
 int tc_codebook_create(int device, const float* E_dev, int64_t n_rows, int latent, int max_batch, TcCodebook** out);
 void tc_codebook_destroy(TcCodebook* h);
 int tc_codebook_match(TcCodebook* h, const float* E_dev, const float* z_dev, int B, int64_t row_offset, int num_cyclo, int upright,

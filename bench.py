@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- pose queries/sec (encode + codebook NN) on 128x128 crops (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision simt|tc]
+
+One "step" = one batch of 256 synthetic uint8 crops through the hot path: conv encoder -> latent -> fused
+L2-normalise + cosine match against the 92 232-row codebook -> (score, index) per crop  (BASELINE.json configs[1]).
+N > 1 (torchrun, one rank per GPU): independent replicas, every rank runs the same batch size ("weak" scaling); no
+data-path collective (queries are independent -- SURVEY.md section 8e row 1).
+
+Printed JSON (rank 0, one line):
+  value      whole-job queries/s with the crops already resident in HBM, device-timed (CUDA events per step, L2 flushed
+             between steps, max over ranks)
+  e2e        same metric through the public plugin call (Codebook.nearest_rotation) with HOST buffers: pinned H2D of the
+             crops and D2H of the indices inside the timed region
+  roofline   dominant kernel (largest share of the step): algorithmic FLOPs / measured duration vs MEASURED_PEAKS.json
+  roofline_match   the fused codebook kernel against the HBM roofline
+  cpu_baseline     the CPU oracle (restated reference path, B=1 per call like the reference) on this box's cores
+--impl reference times that CPU path as the whole arm (TensorFlow is not installable offline: oracle port).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 256
+N_ROWS = 92232
+LATENT = 128
+ENC_FLOP_PER_CROP = 2 * 2140667904
+LAYER_MAC_PER_CROP = [39321600, 838860800, 838860800, 419430400, 4194304]
+MATCH_BYTES = N_ROWS * LATENT * 4 + BATCH * LATENT * 4 + BATCH * 8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8: "hw_slowdown",
+                     0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference path
+def cpu_reference_qps(budget_s, batch=1, max_crops=4096):
+    """The reference's own data flow restated on the CPU (oracle/aae_oracle.py; TensorFlow cannot be installed offline):
+    x/255 -> conv encoder -> dense -> l2_normalize -> full [B, N] cosine row(s) -> host argmax, `batch` crops per call
+    (the reference calls session.run once per detection: batch=1)."""
+    import torch
+    from oracle import aae_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    params = O.make_encoder_params(42)
+    E = O.make_codebook(7)
+    crops = O.make_crops_u8(1234, max(batch, 8))
+    O.nearest_rotation_idcs(crops[:batch], params, E)  # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        O.nearest_rotation_idcs(crops[:batch], params, E)
+        done += batch
+        el = time.perf_counter() - t0
+        if el >= budget_s or done >= max_crops:
+            break
+    return done / el, done, el
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    per_step_budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    qps_list, crops_total = [], 0
+    for i in range(args.warmup + args.steps):
+        q, n, el = cpu_reference_qps(per_step_budget, batch=1, max_crops=256)
+        if i >= args.warmup:
+            qps_list.append((n, el))
+            crops_total += n
+    tot_n = sum(n for n, _ in qps_list)
+    tot_t = sum(t for _, t in qps_list)
+    v = tot_n / tot_t
+    out = {"impl": "reference", "metric": "pose queries/sec (encode+codebook NN)", "value": v, "unit": "queries/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "configs[1]: single object, 128x128x3 uint8 crops, encoder + 92232-row codebook NN", "batch_per_call": 1,
+                      "note": "restated reference CPU path (oracle port; TensorFlow not installable offline), one crop per call like "
+                              "AePoseEstimator.process"},
+           "cpu_baseline": {"value": v, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": "%d crops per step, B=1 per call, torch CPU fp32, %d threads" % (tot_n // max(1, args.steps), os.cpu_count())},
+           "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------- ours
+def run_ours(args, rank, world, local_rank):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    from augmentedautoencoder_b200 import _lib, build_ext
+    if rank == 0:
+        build_ext.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    from augmentedautoencoder_b200.ae.codebook import Codebook
+    from augmentedautoencoder_b200.ae.encoder import Encoder
+    from augmentedautoencoder_b200.ae.session import Session, placeholder
+
+    precision = {"simt": _lib.PREC_FP32_SIMT, "tc": _lib.PREC_TC_SPLIT}[args.precision]
+    rng = np.random.RandomState(42)
+    sess = Session(device=local_rank)
+    x_ph = placeholder(np.float32, [None, 128, 128, 3])
+    enc = Encoder(x_ph, LATENT, [128, 256, 512, 512], 5, [2, 2, 2, 2], False, precision=precision, max_batch=BATCH, seed=42)
+
+    class DS:
+        embedding_size = N_ROWS
+        _kw = {"num_cyclo": "36"}
+        viewsphere_for_embedding = np.zeros((N_ROWS, 3, 3))
+    cb = Codebook(enc, DS(), True, max_batch=BATCH, precision=precision)
+    E = rng.standard_normal((N_ROWS, LATENT))
+    E = (E / np.linalg.norm(E, axis=1, keepdims=True)).astype(np.float32)
+    E[35::36] = E[0::36]
+    cb.embedding_normalized.assign(E)
+
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    n_ring = 4
+    host_crops = [torch.randint(0, 256, (BATCH, 128, 128, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_ring)]
+    dev_crops = [c.to(dev) for c in host_crops]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    lib = _lib.lib()
+    enc_h, cb_h = enc.handle(dev), cb.handle(dev)
+
+    def step_device(i):
+        return cb.nearest_idx_device(dev_crops[i % n_ring])
+
+    # ---- warm-up (also builds handles / packs operands) ----
+    for i in range(args.warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- timed: device-resident inputs, per-step CUDA events, L2 flushed between steps ----
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = lib.aae_launch_count()
+    evs = []
+    for i in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_device(i)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = lib.aae_launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+
+    # ---- e2e: public plugin call with host buffers (pinned H2D + D2H inside the timed region) ----
+    for i in range(2):
+        cb.nearest_rotation(sess, host_crops[i % n_ring], return_idcs=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_e2e = []
+    for i in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        idcs = cb.nearest_rotation(sess, host_crops[i % n_ring], return_idcs=True)  # returns numpy on the host
+        t_e2e.append(time.perf_counter() - t0)
+    assert idcs.shape == (BATCH,)
+    e2e_s = torch.tensor([sum(t_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- per-stage device timing for the roofline lines (separate profiled passes, cudaEvents inside the library) ----
+    buf = (C.c_float * 16)()
+    lib.aae_encoder_profile(enc_h, 1, None, 0)
+    lib.aae_codebook_profile(cb_h, 1, None, 0)
+    enc_stage, match_ms = [], []
+    for i in range(max(3, min(args.steps, 10))):
+        flush.zero_()
+        step_device(i)
+        torch.cuda.synchronize()
+        n = lib.aae_encoder_profile(enc_h, 1, buf, 16)
+        enc_stage.append([buf[j] for j in range(n)])
+        n = lib.aae_codebook_profile(cb_h, 1, buf, 16)
+        match_ms.append(buf[0] if n > 0 else float("nan"))
+    lib.aae_encoder_profile(enc_h, 0, None, 0)
+    lib.aae_codebook_profile(cb_h, 0, None, 0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ms_per_step = total_ms / args.steps
+    value = world * BATCH * args.steps / (total_ms * 1e-3)
+    stage_med = [statistics.median(col) for col in zip(*enc_stage)] if enc_stage and enc_stage[0] else []
+    roof = None
+    if stage_med:
+        dom = int(np.argmax(stage_med))
+        flops = 2.0 * LAYER_MAC_PER_CROP[dom] * BATCH
+        ach = flops / (stage_med[dom] * 1e-3) / 1e12
+        peak = pk["tf_burst"]
+        names = ["conv1 (3->128)", "conv2 (128->256)", "conv3 (256->512)", "conv4 (512->512)", "dense (32768->128)"]
+        roof = {"kernel": "encoder " + names[dom], "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "peak_source": pk["src"] + " bf16 burst", "stage_ms": stage_med,
+                "share_of_step": stage_med[dom] / ms_per_step,
+                "note": "algorithmic FLOPs (2*MAC) of the layer / cudaEvent duration; precision=%s" % args.precision}
+    mm = statistics.median(match_ms) if match_ms else float("nan")
+    ach_b = MATCH_BYTES / (mm * 1e-3) / 1e9
+    roof_match = {"kernel": "fused codebook match (l2norm + scores + argmax)", "bound": "hbm", "achieved": ach_b, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                  "frac": ach_b / pk["hbm_gbs"], "traffic": None, "ms": mm, "bytes": MATCH_BYTES, "peak_source": pk["src"]}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        q1, n1, t1 = cpu_reference_qps(12.0, batch=1)
+        q64, n64, t64 = cpu_reference_qps(6.0, batch=64)
+        cpu = {"value": q1, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "%d crops in %.1f s, one crop per call (reference calling pattern), torch CPU fp32 oracle; batched B=64: %.1f queries/s"
+                         % (n1, t1, q64)}
+    out = {"metric": "pose queries/sec (encode+codebook NN)", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32" if args.precision == "simt" else "f32 via split-fp16 tensor-core products (3x, fp32 accumulate)",
+           "data": "synthetic",
+           "config": {"workload": "configs[1]: single object, batch=256 synthetic 128x128x3 uint8 crops, encoder + fused codebook NN (92232 rows)",
+                      "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": "dp%d (independent replicas)" % world,
+                      "l2": "256 MiB memset between timed steps (untimed) so weights/codebook/crops come from HBM",
+                      "precision": args.precision},
+           "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": BATCH * 128 * 128 * 3,
+                   "d2h_bytes_per_step": BATCH * 4, "api": "Codebook.nearest_rotation(session, pinned uint8 crops, return_idcs=True)"},
+           "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "roofline_match": roof_match,
+           "cpu_baseline": cpu}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("AAE_BENCH_PRECISION", "simt"), choices=["simt", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,11 @@ AAE_API int aae_encoder_forward_f32(aae_encoder* h, const float* crops_dev, int 
  * forward; layer == num_layers gives the flattened encoder_out.  For tests and for the trainer. */
 AAE_API int aae_encoder_activation(aae_encoder* h, int layer, const float** ptr_dev, int64_t* count);
 
+/* Device-side stage timing for benchmarks: `enable` switches cudaEvent bracketing of the stages of the NEXT forward calls
+ * on/off; if stage_ms_out != NULL the stage durations of the LAST profiled forward are written first (conv layers in
+ * order, then the dense layer) and their count is returned (>= 0; negative = error). */
+AAE_API int aae_encoder_profile(aae_encoder* h, int enable, float* stage_ms_out, int capacity);
+
 /* ---------------------------------------------------------------- Codebook -----------------
  * Replaces the Codebook graph: tf.nn.l2_normalize(z,1), matmul(zq, embedding_normalized^T),
  * argmax (auto_pose/ae/codebook.py:27,50-51) and the host-side np.argmax / strided argmax /
@@ -123,6 +128,8 @@ AAE_API int aae_codebook_cosine(aae_codebook* h, const float* z_dev, int batch, 
 AAE_API int aae_topk_merge(const float* scores_dev, const int32_t* idx_dev, int n_shards, int batch, int k,
                            float* scores_out_dev, int32_t* idx_out_dev, void* stream);
 AAE_API int64_t aae_codebook_rows(const aae_codebook* h);
+/* Same contract as aae_encoder_profile; one stage: the whole fused match (k = 1). */
+AAE_API int aae_codebook_profile(aae_codebook* h, int enable, float* stage_ms_out, int capacity);
 
 /* ---------------------------------------------------------------- Decoder + loss -----------
  * Replaces Decoder.x: dense latent->8*8*512 + ReLU, 3x [NN-resize x2, conv5x5 s1 + ReLU],

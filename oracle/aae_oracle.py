@@ -108,9 +108,19 @@ def make_decoder_params(seed: int = 43, num_filters=NUM_FILTER, ksize=KSIZE, lat
     return p
 
 
-def make_crops_u8(seed: int, batch: int, hw: int = H, ch: int = C) -> np.ndarray:
-    """i.i.d. U{0..255} BGR crops, NHWC uint8 (auto_pose/ae/ae_factory.py:133 placeholder shape)."""
-    return np.random.RandomState(seed).randint(0, 256, size=(batch, hw, hw, ch), dtype=np.uint8)
+def make_crops_u8(seed: int, batch: int, hw: int = H, ch: int = C, structured: bool = True) -> np.ndarray:
+    """Synthetic BGR crops, NHWC uint8 (auto_pose/ae/ae_factory.py:133 placeholder shape).  structured=True draws a
+    different coarse random pattern per crop (8x8 blocks + pixel noise) so that the latents -- and therefore the
+    matched codebook rows -- differ from crop to crop; structured=False is i.i.d. U{0..255} (every crop then encodes
+    to almost the same latent)."""
+    rng = np.random.RandomState(seed)
+    if not structured:
+        return rng.randint(0, 256, size=(batch, hw, hw, ch), dtype=np.uint8)
+    cells = max(hw // 16, 1)
+    coarse = rng.randint(0, 256, size=(batch, cells, cells, ch)).astype(np.int32)
+    img = np.repeat(np.repeat(coarse, hw // cells, axis=1), hw // cells, axis=2)
+    img = img + rng.randint(-40, 41, size=(batch, hw, hw, ch))
+    return np.clip(img, 0, 255).astype(np.uint8)
 
 
 def make_codebook(seed: int, n: int = N_CODEBOOK, j: int = LATENT, num_cyclo: int = NUM_CYCLO,

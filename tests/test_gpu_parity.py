@@ -186,8 +186,9 @@ def test_topk_merge_equals_unsharded(sess):
     scores = -np.sort(-scores, axis=2)
     idx = np.stack([np.sort(rng.choice(1000, size=(B, k), replace=False), axis=1) + s * 1000 for s in range(S)]).astype(np.int32)
     so, io = torch.empty((B, k), device="cuda"), torch.empty((B, k), dtype=torch.int32, device="cuda")
-    _lib.check(_lib.lib().aae_topk_merge(_lib.ptr(torch.from_numpy(scores).cuda()), _lib.ptr(torch.from_numpy(idx).cuda()), S, B, k,
-                                         _lib.ptr(so), _lib.ptr(io), None))
+    sd, idd = torch.from_numpy(scores).cuda(), torch.from_numpy(idx).cuda()  # keep the device tensors alive across the call
+    _lib.check(_lib.lib().aae_topk_merge(_lib.ptr(sd), _lib.ptr(idd), S, B, k, _lib.ptr(so), _lib.ptr(io), None))
+    torch.cuda.synchronize()
     so, io = so.cpu().numpy(), io.cpu().numpy()
     for b in range(B):
         pairs = sorted(((-scores[s, b, j], idx[s, b, j]) for s in range(S) for j in range(k)))[:k]
@@ -262,7 +263,8 @@ def test_bootstrap_loss_tie_handling_and_gradient(sess):
     rng = np.random.RandomState(0)
     xb = rng.rand(B, n).astype(np.float32)
     yb = rng.rand(B, n).astype(np.float32)
-    yb[1] = xb[1] + 0.25  # every squared error identical: ties everywhere -> the first k elements are selected
+    xb[1] = rng.randint(0, 128, n).astype(np.float32) / 256.0  # exactly representable, so that ...
+    yb[1] = xb[1] + 0.25  # ... every squared error is identical: ties everywhere -> the first k elements are selected
     loss, grad = Decoder.loss_device(torch.from_numpy(xb).cuda(), torch.from_numpy(yb).cuda(), 4, with_grad=True)
     k = n // 4
     l2 = (yb - xb) ** 2
@@ -316,9 +318,15 @@ def test_full_size_training_forward_backward(sess):
     xb = np.random.RandomState(3).rand(2, 128, 128, 3).astype(np.float32)
     yb = np.random.RandomState(4).rand(2, 128, 128, 3).astype(np.float32)
     loss = top.step_device(torch.from_numpy(xb).cuda(), torch.from_numpy(yb).cuda(), update=False)
-    loss_ref, _, g = O.ae_forward_loss(xb, yb, ep, dp, with_grads=True)
-    assert abs(float(loss) - loss_ref) < 1e-6
+    loss_ref, _, g32 = O.ae_forward_loss(xb, yb, ep, dp, with_grads=True)
+    loss64, _, g64 = O.ae_forward_loss(xb, yb, ep, dp, dtype=torch.float64, with_grads=True)
+    assert abs(float(loss) - loss64) < 1e-6
     grads = top.gradients(sess.device)
-    for name, gr in g.items():
-        scale = max(np.abs(gr).max(), 1e-8)
-        assert np.max(np.abs(grads[name] - gr)) < 1e-3 * scale + 1e-9, name
+    # ReLU masks and the top-k threshold are discrete decisions: elements within fp32 rounding of a boundary may fall on
+    # either side in any fp32 implementation.  Bar: our error against the float64 truth is no worse than 3x the error the
+    # fp32 CPU restatement (the TF stand-in) makes against the same truth.
+    for name, gr in g64.items():
+        scale = max(np.abs(gr).max(), 1e-12)
+        err_ours = np.max(np.abs(grads[name] - gr)) / scale
+        err_cpu32 = np.max(np.abs(g32[name] - gr)) / scale
+        assert err_ours < max(3 * err_cpu32, 2e-4), (name, err_ours, err_cpu32)
