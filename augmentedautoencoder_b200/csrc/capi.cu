@@ -307,6 +307,7 @@ extern "C" int aae_encoder_set_weights(aae_encoder* h, int layer, const float* k
   if (kernel_any) AAE_TRY(copy_any(w.p, kernel_any, w.n * sizeof(float), s));
   if (bias_any) AAE_TRY(copy_any(b.p, bias_any, b.n * sizeof(float), s));
   if (h->tc && kernel_any) AAE_TRY(tc_encoder_pack_weights(h->tc, layer, w.p, s));
+  if (h->tc) AAE_TRY(tc_encoder_set_bias(h->tc, layer, b.p));
   AAE_CUDA_OK(cudaStreamSynchronize(s));  // host source buffers may be freed by the caller on return
   return AAE_OK;
 }
@@ -366,7 +367,10 @@ extern "C" int aae_encoder_forward_f32(aae_encoder* h, const float* crops_dev, i
 extern "C" int aae_encoder_activation(aae_encoder* h, int layer, const float** ptr_dev, int64_t* count) {
   AAE_REQUIRE(h != nullptr && ptr_dev != nullptr && count != nullptr, "null argument");
   AAE_REQUIRE(layer >= 0 && layer <= (int)h->conv.size(), "layer %d out of range", layer);
-  AAE_REQUIRE(!h->last_was_tc, "fp32 NHWC activations are only kept by the AAE_PREC_FP32_SIMT path");
+  if (h->last_was_tc) {
+    DeviceGuard g(h->device);
+    return tc_encoder_activation(h->tc, std::min(layer, (int)h->conv.size() - 1), h->last_batch, ptr_dev, count, nullptr);
+  }
   const ConvLayer& L = h->conv[std::min(layer, (int)h->conv.size() - 1)];
   *ptr_dev = L.out.p;
   *count = (int64_t)h->last_batch * L.out_h * L.out_w * L.out_c;
@@ -457,7 +461,7 @@ extern "C" int aae_codebook_match(aae_codebook* h, const float* z_dev, int batch
   DeviceGuard g(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   if (k == 1) {
-    if (h->tc) {
+    if (h->tc && !upright) {
       h->timer.reset();
       h->timer.mark(s);
       AAE_TRY(tc_codebook_match(h->tc, h->E.p, z_dev, batch, h->row_offset, h->num_cyclo, upright, scores_out_dev, idx_out_dev, s));

@@ -1,5 +1,6 @@
 // Internal helpers shared by the translation units of libaae_b200.so (not part of the C ABI).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -87,6 +88,12 @@ struct IGemmParams {
   int M, K;             // GEMM sizes
   int k_per_split;      // K range handled per blockIdx.z (multiple of 16); gridDim.z splits
   int parity_major;     // DGRAD with stride 2: m enumerates pixels parity-class-major (ph,pw,n,i,j)
+  // optional split-fp16 output for the tensor-core path (FWD only): value * split_scale -> (hi, lo) fp16, written in the
+  // consumer's space-to-depth layout [b, h/2, w/2, (h%2, w%2, c)] when split_s2d, else plain NHWC
+  __half* split_hi;
+  __half* split_lo;
+  float split_scale;
+  int split_s2d;
 };
 
 int launch_igemm(const IGemmParams& p, int mode, cudaStream_t stream);

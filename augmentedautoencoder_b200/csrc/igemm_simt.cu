@@ -280,7 +280,30 @@ __global__ void __launch_bounds__(NT) igemm_f32_kernel(const IGemmParams p) {
           v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
         }
       }
-      *reinterpret_cast<float4*>(cbase + row * p.N + n) = make_float4(v[0], v[1], v[2], v[3]);
+      if (MODE == GATHER_FWD && p.split_hi != nullptr) {
+        long long o = row * p.N + n;
+        if (p.split_s2d) {
+          const PixCoord pc = decode_pixel(p, m, p.M);
+          o = ((long long)(pc.n * (p.PH >> 1) + (pc.ph >> 1)) * (p.PW >> 1) + (pc.pw >> 1)) * (4LL * p.N) +
+              (((pc.ph & 1) << 1) | (pc.pw & 1)) * p.N + n;
+        }
+        __half h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float x = v[j] * p.split_scale;
+          h[j] = __float2half_rn(x);
+          l[j] = __float2half_rn(x - __half2float(h[j]));
+        }
+        uint2 hv, lv;
+        hv.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+        hv.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+        lv.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+        lv.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+        *reinterpret_cast<uint2*>(p.split_hi + o) = hv;
+        *reinterpret_cast<uint2*>(p.split_lo + o) = lv;
+      } else {
+        *reinterpret_cast<float4*>(cbase + row * p.N + n) = make_float4(v[0], v[1], v[2], v[3]);
+      }
     }
   }
 }

@@ -14,6 +14,8 @@ int tc_encoder_pack_weights(TcEncoder* h, int layer, const float* w_dev, cudaStr
 int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const float* w0, const float* b0, const float* dense_b,
                        float* z_out, cudaStream_t s);
 
+int tc_encoder_set_bias(TcEncoder* h, int layer, const float* bias_dev);
+int tc_encoder_activation(TcEncoder* h, int layer, int B, const float** ptr, int64_t* count, cudaStream_t s);
 void tc_encoder_enable_timer(TcEncoder* h, bool on);
 int tc_encoder_read_timer(TcEncoder* h, float* ms, int cap);
 

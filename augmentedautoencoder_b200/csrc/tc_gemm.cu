@@ -1,0 +1,538 @@
+// tcgen05 implicit-GEMM for the encoder's dense contractions (AAE_PREC_TC_SPLIT).
+//
+//   D[128 output pixels x N_TILE channels] (fp32, TMEM) += A[128 x 64] * W[N_TILE x 64]^T   per K chunk of 64 input channels
+//
+// Replaces tf.layers.conv2d(k=5, stride 2, padding='same') + ReLU and tf.layers.dense of
+// auto_pose/ae/encoder.py:43-50,62-66 for every layer with Cin % 64 == 0 (conv2..conv4, dense).
+//
+// fp32-grade arithmetic on fp16 tensor cores: every fp32 operand x is stored as two fp16 terms, hi = rn(x) and
+// lo = rn(x - hi) (22 significant bits; operands pre-scaled by a power of two so lo stays a normal fp16), and each
+// K chunk issues three MMAs  hi*hi + hi*lo + lo*hi  into the same fp32 TMEM accumulator.
+//
+// Data movement: activations live in HBM in a space-to-depth layout  Xs[b, h/2, w/2, (h%2, w%2, c)]  written by the
+// producing layer's epilogue, so that tap (kh, kw) of the stride-2 / asymmetric-SAME(1,2) convolution is a plain
+// unit-stride 4-D TMA box  [64 ch, BW, BH, BB]  at offset (di, dj) with zero fill outside the image -- no im2col
+// buffer, no stride-2 gathers.  Weights are pre-packed [Cout][25*Cin] K-major.  Both operands land in shared memory in
+// the 128-byte-swizzle canonical layout tcgen05.mma consumes directly.
+//
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+// (TMEM -> registers -> bias/ReLU -> hi/lo split -> global, in the next layer's space-to-depth layout).
+#include <algorithm>
+#include <vector>
+
+#include "tc.cuh"
+#include "tc_common.cuh"
+
+namespace aae {
+
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------- host helpers
+PFN_tmapEncodeTiled get_tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_tmapEncodeTiled enc = get_tmap_encoder();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return AAE_ERR_CUDA; }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return AAE_ERR_CUDA; }
+  return AAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- kernel
+enum TcOutMode : int { OUT_S2D_SPLIT = 0, OUT_PLAIN_SPLIT = 1, OUT_F32 = 2 };
+
+struct TcGemmParams {
+  int M;                 // valid output rows (pixels, or batch rows for the dense layer)
+  int N;                 // total output channels
+  int OH, OW;            // output spatial dims (1,1 for dense)
+  int BW, BH;            // pixel box of one 128-row tile: BW*BH*BB = 128
+  int taps;              // 25 (conv) or 1 (dense)
+  int chunks_per_tap;    // Cin / 64
+  int iters_per_split;   // K iterations (tap, chunk) handled per blockIdx.z
+  int8_t tap_di[32], tap_dj[32];
+  int tap_ch[32];        // channel offset of the tap's parity plane in the space-to-depth tensor
+  float unscale;         // 1 / (scale_A * scale_W)
+  float out_scale;       // scale applied before the hi/lo split of the output (next layer's scale_A)
+  const float* bias;
+  int relu;
+  int out_mode;
+  __half* out_hi;
+  __half* out_lo;
+  float* out_f32;        // OUT_F32: [splits, M, N]
+};
+
+template <int N_TILE, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = 128 * 128;            // 128 rows x 64 fp16
+  static constexpr int W_BYTES = N_TILE * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const TcGemmParams p) {
+  using S = TcSmem<N_TILE, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int n0 = blockIdx.y * N_TILE;
+  const int total_iters = p.taps * p.chunks_per_tap;
+  const int it_begin = blockIdx.z * p.iters_per_split;
+  const int it_end = min(total_iters, it_begin + p.iters_per_split);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<N_TILE>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int hw = p.OH * p.OW;
+      const int b0 = m0 / hw, rem = m0 - b0 * hw;
+      const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
+      for (int it = it_begin, i = 0; it < it_end; ++it, ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int tap = it / p.chunks_per_tap, cc = it - tap * p.chunks_per_tap;
+        uint8_t* st = smem + s * S::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        const int c0 = p.tap_ch[tap] + cc * 64;
+        const int x = ow0 + p.tap_dj[tap], y = oh0 + p.tap_di[tap];
+        tma_load_4d(st, &tm_a_hi, &full_bar[s], c0, x, y, b0);
+        tma_load_4d(st + S::A_BYTES, &tm_a_lo, &full_bar[s], c0, x, y, b0);
+        const int kcol = it * 64;
+        tma_load_2d(st + 2 * S::A_BYTES, &tm_w_hi, &full_bar[s], kcol, n0);
+        tma_load_2d(st + 2 * S::A_BYTES + S::W_BYTES, &tm_w_lo, &full_bar[s], kcol, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, N_TILE, 0);
+      for (int it = it_begin, i = 0; it < it_end; ++it, ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint64_t a_hi = make_sw128_kmajor_desc(st);
+        const uint64_t a_lo = make_sw128_kmajor_desc(st + S::A_BYTES);
+        const uint64_t w_hi = make_sw128_kmajor_desc(st + 2 * S::A_BYTES);
+        const uint64_t w_lo = make_sw128_kmajor_desc(st + 2 * S::A_BYTES + S::W_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // small cross terms first, the dominant hi*hi product last
+          umma_f16(tmem_base, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
+          umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_hi, k), idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int m = m0 + r;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool valid = m < p.M;
+    long long row_off = 0;
+    if (valid) {
+      if (p.out_mode == OUT_S2D_SPLIT) {
+        const int hw = p.OH * p.OW;
+        const int b = m / hw, rem = m - b * hw;
+        const int oh = rem / p.OW, ow = rem - oh * p.OW;
+        row_off = ((long long)(b * (p.OH >> 1) + (oh >> 1)) * (p.OW >> 1) + (ow >> 1)) * (4LL * p.N) + (((oh & 1) << 1) | (ow & 1)) * p.N;
+      } else {
+        row_off = (long long)m * p.N;
+      }
+    }
+    const bool has_work = it_end > it_begin;
+#pragma unroll 1
+    for (int c = 0; c < N_TILE / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      if (!valid) continue;
+      const int n = n0 + c * 32;
+      if (n >= p.N) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = has_work ? __uint_as_float(v[j]) * p.unscale : 0.f;
+      if (p.out_mode == OUT_F32) {
+        float* dst = p.out_f32 + (long long)blockIdx.z * p.M * p.N + row_off + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      } else {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a = f[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+          float b = f[j + 1] + (p.bias ? __ldg(p.bias + n + j + 1) : 0.f);
+          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          a *= p.out_scale; b *= p.out_scale;
+          __half ah, al, bh, bl;
+          split_f16(a, ah, al);
+          split_f16(b, bh, bl);
+          hi[j >> 1] = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
+          lo[j >> 1] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+        }
+        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + row_off + n);
+        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + row_off + n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<N_TILE>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- packing kernels
+namespace {
+
+// W fp32 [taps][Cin][Cout] (HWIO flattened) -> Wp_{hi,lo} fp16 [Cout][taps*Cin], value scaled by `scale`
+__global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, float scale, __half* __restrict__ hi,
+                                    __half* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ci = ci0 + i, co = co0 + threadIdx.x;
+    tile[i][threadIdx.x] = (ci < cin && co < cout) ? w[((long long)tap * cin + ci) * cout + co] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int co = co0 + i, ci = ci0 + threadIdx.x;
+    if (co < cout && ci < cin) {
+      __half h, l;
+      split_f16(tile[threadIdx.x][i] * scale, h, l);
+      const long long o = (long long)co * taps * cin + (long long)tap * cin + ci;
+      hi[o] = h;
+      lo[o] = l;
+    }
+  }
+}
+
+// (hi, lo) fp16 activations -> fp32 NHWC (undoing the space-to-depth layout and the scale); debug / test visibility only
+__global__ void unpack_act_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int B, int H, int W, int C, int s2d,
+                                  float inv_scale, float* __restrict__ out) {
+  const long long total = (long long)B * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    long long src = i;
+    if (s2d) src = ((long long)(b * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * (4LL * C) + (((h & 1) << 1) | (w & 1)) * C + c;
+    out[i] = (__half2float(hi[src]) + __half2float(lo[src])) * inv_scale;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------- encoder plan
+constexpr float ACT_SCALE = 16.f;     // activations (and the [0,1] input) are stored as 16 * x
+constexpr float W_SCALE = 256.f;      // weights are stored as 256 * w
+constexpr int TC_N_TILE = 256;
+constexpr int TC_STAGES = 2;
+
+struct TcLayer {
+  int in_h, in_w, in_c, out_h, out_w, out_c;   // conv geometry (input is the space-to-depth tensor [B, in_h/2, in_w/2, 4*in_c])
+  int taps, BW, BH, BB;
+  __half *in_hi = nullptr, *in_lo = nullptr;    // activations entering this layer
+  __half *w_hi = nullptr, *w_lo = nullptr;      // packed weights [out_c][taps*in_c]
+  CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo;
+  TcGemmParams gp;
+  int n_tile;
+};
+
+struct TcEncoder {
+  int device;
+  aae_net_cfg cfg;
+  std::vector<TcLayer> layers;   // conv layers 1..L-1 followed by the dense layer
+  int flat;
+  float* partials = nullptr;     // dense split-K partials [splits, max_batch, latent]
+  int dense_splits = 1;
+  float* dbg = nullptr;          // fp32 view of an activation (tests)
+  size_t dbg_floats = 0;
+  bool timer_on = false;
+  std::vector<cudaEvent_t> ev;
+  int ev_used = 0;
+};
+
+namespace {
+
+template <int N_TILE, int STAGES>
+int launch_tc_gemm(const TcLayer& L, dim3 grid, cudaStream_t s) {
+  using S = TcSmem<N_TILE, STAGES>;
+  auto kern = tc_gemm_kernel<N_TILE, STAGES>;
+  AAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  kern<<<grid, 256, S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w_hi, L.tm_w_lo, L.gp);
+  AAE_LAUNCH_OK();
+  return AAE_OK;
+}
+
+int dev_alloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) { *p = nullptr; set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return AAE_ERR_OOM; }
+  cudaMemset(*p, 0, bytes);
+  return AAE_OK;
+}
+
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace
+
+int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
+  *out = nullptr;
+  const int L = cfg->num_layers;
+  AAE_REQUIRE(aae_device_supported(device), "AAE_PREC_TC_SPLIT needs a compute-capability 10.x device (tcgen05/TMEM)");
+  AAE_REQUIRE(L >= 2, "AAE_PREC_TC_SPLIT: at least two conv layers expected");
+  TcEncoder* h = new TcEncoder();
+  h->device = device;
+  h->cfg = *cfg;
+  int ih = (cfg->in_h + cfg->strides[0] - 1) / cfg->strides[0], iw = (cfg->in_w + cfg->strides[0] - 1) / cfg->strides[0], ic = cfg->filters[0];
+  const int B = cfg->max_batch;
+  int st = AAE_OK;
+  for (int l = 1; l <= L && st == AAE_OK; ++l) {
+    TcLayer T;
+    memset(&T.gp, 0, sizeof(T.gp));
+    const bool dense = (l == L);
+    if (!dense) {
+      if (cfg->strides[l] != 2 || cfg->kernel_size != 5 || (ih & 1) || (iw & 1) || ic % 64 != 0 || cfg->filters[l] % 32 != 0) {
+        set_error("AAE_PREC_TC_SPLIT: layer %d unsupported (needs k=5, stride 2, even dims, Cin %% 64 == 0, Cout %% 32 == 0)", l);
+        st = AAE_ERR_UNSUPPORTED;
+        break;
+      }
+      T.in_h = ih; T.in_w = iw; T.in_c = ic;
+      T.out_h = ih / 2; T.out_w = iw / 2; T.out_c = cfg->filters[l];
+      T.taps = 25;
+      if (!pow2(T.out_w) || !pow2(T.out_h) || T.out_w > 128) { set_error("AAE_PREC_TC_SPLIT: output dims must be powers of two <= 128"); st = AAE_ERR_UNSUPPORTED; break; }
+      T.BW = T.out_w;
+      T.BH = std::min(T.out_h, 128 / T.BW);
+      T.BB = 128 / (T.BW * T.BH);
+    } else {
+      T.in_h = T.in_w = 1; T.in_c = ih * iw * ic;
+      T.out_h = T.out_w = 1; T.out_c = cfg->latent;
+      T.taps = 1; T.BW = 1; T.BH = 1; T.BB = 128;
+      h->flat = T.in_c;
+      if (T.in_c % 64 != 0 || T.out_c % 32 != 0) { set_error("AAE_PREC_TC_SPLIT: dense layer needs flat %% 64 == 0 and latent %% 32 == 0"); st = AAE_ERR_UNSUPPORTED; break; }
+    }
+    T.n_tile = T.out_c >= 256 ? 256 : 128;
+    // batch dimension padded to a whole number of TMA boxes, so a tile never addresses rows outside the tensor map
+    const int B_pad = (int)ceil_div(B, T.BB) * T.BB;
+    const size_t act_alloc = (size_t)B_pad * T.in_h * T.in_w * T.in_c;
+    if ((st = dev_alloc((void**)&T.in_hi, act_alloc * sizeof(__half))) != AAE_OK) break;
+    if ((st = dev_alloc((void**)&T.in_lo, act_alloc * sizeof(__half))) != AAE_OK) break;
+    const size_t w_elems = (size_t)T.out_c * T.taps * T.in_c;
+    if ((st = dev_alloc((void**)&T.w_hi, w_elems * sizeof(__half))) != AAE_OK) break;
+    if ((st = dev_alloc((void**)&T.w_lo, w_elems * sizeof(__half))) != AAE_OK) break;
+    // ---- tensor maps ----
+    if (!dense) {
+      const uint64_t C4 = 4ull * T.in_c, W2 = T.in_w / 2, H2 = T.in_h / 2;
+      const uint64_t dims[4] = {C4, W2, H2, (uint64_t)B_pad};
+      const uint64_t strides[3] = {C4 * 2, W2 * C4 * 2, H2 * W2 * C4 * 2};
+      const uint32_t box[4] = {64, (uint32_t)T.BW, (uint32_t)T.BH, (uint32_t)T.BB};
+      if ((st = make_tmap_f16(&T.tm_a_hi, T.in_hi, 4, dims, strides, box)) != AAE_OK) break;
+      if ((st = make_tmap_f16(&T.tm_a_lo, T.in_lo, 4, dims, strides, box)) != AAE_OK) break;
+    } else {
+      const uint64_t dims[4] = {(uint64_t)T.in_c, 1, 1, (uint64_t)B_pad};
+      const uint64_t strides[3] = {(uint64_t)T.in_c * 2, (uint64_t)T.in_c * 2, (uint64_t)T.in_c * 2};
+      const uint32_t box[4] = {64, 1, 1, 128};
+      if ((st = make_tmap_f16(&T.tm_a_hi, T.in_hi, 4, dims, strides, box)) != AAE_OK) break;
+      if ((st = make_tmap_f16(&T.tm_a_lo, T.in_lo, 4, dims, strides, box)) != AAE_OK) break;
+    }
+    {
+      const uint64_t K = (uint64_t)T.taps * T.in_c;
+      const uint64_t dims[2] = {K, (uint64_t)T.out_c};
+      const uint64_t strides[1] = {K * 2};
+      const uint32_t box[2] = {64, (uint32_t)std::min(T.n_tile, T.out_c)};
+      if ((st = make_tmap_f16(&T.tm_w_hi, T.w_hi, 2, dims, strides, box)) != AAE_OK) break;
+      if ((st = make_tmap_f16(&T.tm_w_lo, T.w_lo, 2, dims, strides, box)) != AAE_OK) break;
+    }
+    // ---- static GEMM parameters ----
+    TcGemmParams& g = T.gp;
+    g.N = T.out_c; g.OH = T.out_h; g.OW = T.out_w; g.BW = T.BW; g.BH = T.BH;
+    g.taps = T.taps; g.chunks_per_tap = T.in_c / 64;
+    g.iters_per_split = g.taps * g.chunks_per_tap;
+    for (int t = 0; t < T.taps; ++t) {
+      if (dense) { g.tap_di[t] = 0; g.tap_dj[t] = 0; g.tap_ch[t] = 0; continue; }
+      const int kh = t / 5, kw = t % 5;
+      // input row 2*oh + kh - 1 (TF SAME pads 1 before): block offset (kh+1)/2 - 1, parity (kh+1) % 2
+      g.tap_di[t] = (int8_t)((kh + 1) / 2 - 1);
+      g.tap_dj[t] = (int8_t)((kw + 1) / 2 - 1);
+      g.tap_ch[t] = ((((kh + 1) & 1) << 1) | ((kw + 1) & 1)) * T.in_c;
+    }
+    g.unscale = 1.f / (ACT_SCALE * W_SCALE);
+    g.out_scale = ACT_SCALE;
+    g.relu = dense ? 0 : 1;
+    h->layers.push_back(T);
+    if (!dense) { ih = T.out_h; iw = T.out_w; ic = T.out_c; }
+  }
+  if (st == AAE_OK) {
+    // wire outputs: layer i writes the input buffers of layer i+1; the last conv writes plain NHWC (the flatten order)
+    for (size_t i = 0; i + 1 < h->layers.size(); ++i) {
+      TcGemmParams& g = h->layers[i].gp;
+      g.out_hi = h->layers[i + 1].in_hi;
+      g.out_lo = h->layers[i + 1].in_lo;
+      g.out_mode = (i + 2 == h->layers.size()) ? OUT_PLAIN_SPLIT : OUT_S2D_SPLIT;
+    }
+    TcLayer& D = h->layers.back();
+    const int total = D.gp.taps * D.gp.chunks_per_tap;
+    h->dense_splits = std::min(total, 74);
+    D.gp.iters_per_split = (total + h->dense_splits - 1) / h->dense_splits;
+    h->dense_splits = (total + D.gp.iters_per_split - 1) / D.gp.iters_per_split;
+    D.gp.out_mode = OUT_F32;
+    st = dev_alloc((void**)&h->partials, (size_t)h->dense_splits * (B + 128) * cfg->latent * sizeof(float));
+    D.gp.out_f32 = h->partials;
+  }
+  if (st != AAE_OK) { tc_encoder_destroy(h); return st; }
+  *out = h;
+  return AAE_OK;
+}
+
+void tc_encoder_destroy(TcEncoder* h) {
+  if (!h) return;
+  for (auto& T : h->layers) { cudaFree(T.in_hi); cudaFree(T.in_lo); cudaFree(T.w_hi); cudaFree(T.w_lo); }
+  cudaFree(h->partials);
+  cudaFree(h->dbg);
+  for (auto e : h->ev) cudaEventDestroy(e);
+  delete h;
+}
+
+int tc_encoder_pack_weights(TcEncoder* h, int layer, const float* w_dev, cudaStream_t s) {
+  if (layer == 0) return AAE_OK;  // conv1 stays on the fp32 SIMT kernel (Cin = 3)
+  AAE_REQUIRE(layer >= 1 && layer <= (int)h->layers.size(), "tc pack: layer %d out of range", layer);
+  TcLayer& T = h->layers[layer - 1];
+  dim3 grid((unsigned)ceil_div(T.out_c, 32), (unsigned)ceil_div(T.in_c, 32), (unsigned)T.taps), block(32, 8);
+  pack_weights_kernel<<<grid, block, 0, s>>>(w_dev, T.taps, T.in_c, T.out_c, W_SCALE, T.w_hi, T.w_lo);
+  AAE_LAUNCH_OK();
+  return AAE_OK;
+}
+
+void tc_encoder_enable_timer(TcEncoder* h, bool on) { h->timer_on = on; }
+
+static void tc_mark(TcEncoder* h, cudaStream_t s) {
+  if (!h->timer_on) return;
+  if (h->ev_used == (int)h->ev.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; h->ev.push_back(e); }
+  cudaEventRecord(h->ev[h->ev_used++], s);
+}
+
+int tc_encoder_read_timer(TcEncoder* h, float* ms, int cap) {
+  int n = 0;
+  if (h->ev_used >= 2) {
+    cudaEventSynchronize(h->ev[h->ev_used - 1]);
+    for (int i = 0; i + 1 < h->ev_used && n < cap; ++i, ++n) cudaEventElapsedTime(&ms[n], h->ev[i], h->ev[i + 1]);
+  }
+  return n;
+}
+
+int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const float* w0, const float* b0, const float* dense_b,
+                       float* z_out, cudaStream_t s) {
+  const aae_net_cfg& cfg = h->cfg;
+  h->ev_used = 0;
+  tc_mark(h, s);
+  {  // conv1 (Cin = 3, K = 75): fp32 SIMT implicit GEMM, epilogue writes conv2's space-to-depth (hi, lo) input directly
+    IGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = crops; p.src_u8 = src_u8;
+    p.B = B; p.SH = cfg.in_h; p.SW = cfg.in_w; p.SC = cfg.in_c;
+    p.PH = h->layers[0].in_h; p.PW = h->layers[0].in_w;
+    p.KH = p.KW = cfg.kernel_size; p.stride = cfg.strides[0];
+    const int tot_h = std::max((p.PH - 1) * p.stride + p.KH - cfg.in_h, 0), tot_w = std::max((p.PW - 1) * p.stride + p.KW - cfg.in_w, 0);
+    p.pad_t = tot_h / 2; p.pad_l = tot_w / 2;
+    p.Bm = w0; p.N = cfg.filters[0]; p.bias = b0; p.act = ACT_RELU;
+    p.M = B * p.PH * p.PW; p.K = p.KH * p.KW * p.SC;
+    p.k_per_split = (int)ceil_div(p.K, 16) * 16;
+    p.split_hi = h->layers[0].in_hi; p.split_lo = h->layers[0].in_lo; p.split_scale = ACT_SCALE; p.split_s2d = 1;
+    AAE_TRY(launch_igemm(p, GATHER_FWD, s));
+  }
+  tc_mark(h, s);
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    TcLayer& T = h->layers[i];
+    const bool dense = (i + 1 == h->layers.size());
+    T.gp.M = dense ? B : B * T.out_h * T.out_w;
+    dim3 grid((unsigned)ceil_div(T.gp.M, 128), (unsigned)ceil_div(T.out_c, T.n_tile), dense ? (unsigned)h->dense_splits : 1u);
+    if (T.n_tile == 256) AAE_TRY((launch_tc_gemm<256, TC_STAGES>(T, grid, s)));
+    else AAE_TRY((launch_tc_gemm<128, 3>(T, grid, s)));
+    if (dense) AAE_TRY(launch_splitk_reduce(h->partials, h->dense_splits, (int64_t)B * cfg.latent, cfg.latent, dense_b, ACT_NONE, z_out, s));
+    tc_mark(h, s);
+  }
+  return AAE_OK;
+}
+
+int tc_encoder_set_bias(TcEncoder* h, int layer, const float* bias_dev) {
+  if (layer >= 1 && layer < (int)h->layers.size()) h->layers[layer - 1].gp.bias = bias_dev;
+  return AAE_OK;
+}
+
+int tc_encoder_activation(TcEncoder* h, int layer, int B, const float** ptr, int64_t* count, cudaStream_t s) {
+  // layer l's output is the input of TcLayer[l] (layers[] starts at conv index 1)
+  AAE_REQUIRE(layer >= 0 && layer < (int)h->layers.size(), "tc activation: layer %d out of range", layer);
+  const TcLayer& T = h->layers[layer];
+  const bool plain = (layer + 1 == (int)h->layers.size());
+  int H, W, C;
+  if (plain) { const TcLayer& P = h->layers[layer - 1]; H = P.out_h; W = P.out_w; C = P.out_c; }
+  else { H = T.in_h; W = T.in_w; C = T.in_c; }
+  const size_t n = (size_t)B * H * W * C;
+  if (h->dbg_floats < n) {
+    cudaFree(h->dbg);
+    h->dbg = nullptr;
+    AAE_TRY(dev_alloc((void**)&h->dbg, n * sizeof(float)));
+    h->dbg_floats = n;
+  }
+  unpack_act_kernel<<<1024, 256, 0, s>>>(T.in_hi, T.in_lo, B, H, W, C, plain ? 0 : 1, 1.f / ACT_SCALE, h->dbg);
+  AAE_LAUNCH_OK();
+  AAE_CUDA_OK(cudaStreamSynchronize(s));
+  *ptr = h->dbg;
+  *count = (int64_t)n;
+  return AAE_OK;
+}
+
+}  // namespace aae
