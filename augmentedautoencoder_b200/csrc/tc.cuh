@@ -6,6 +6,14 @@ namespace aae {
 
 struct TcEncoder;
 struct TcCodebook;
+struct TcConv1;
+
+bool tc_conv1_supported(const aae_net_cfg* cfg);
+int tc_conv1_create(int device, const aae_net_cfg* cfg, TcConv1** out);
+void tc_conv1_destroy(TcConv1* h);
+int tc_conv1_pack(TcConv1* h, const float* w_dev, int K, float w_scale, cudaStream_t s);
+int tc_conv1_forward(TcConv1* h, const aae_net_cfg* cfg, const void* crops, int src_u8, int B, const float* bias, float act_scale,
+                     float w_scale, __half* out_hi, __half* out_lo, cudaStream_t s);
 
 int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out);
 void tc_encoder_destroy(TcEncoder* h);

@@ -1,0 +1,299 @@
+// First encoder layer on tcgen05 (AAE_PREC_TC_SPLIT): conv 5x5 / stride 2 / TF-SAME(1,2), Cin = 3 -> Cout = 128, + bias +
+// ReLU  (auto_pose/ae/encoder.py:43-50, first loop iteration), fused with the x/255. of auto_pose/ae/codebook.py:58-59.
+//
+// K = 25*3 = 75 is far too small and too ragged for TMA (patches overlap, 3-byte pixels), so the A operand is built in
+// shared memory by 128 "builder" threads -- one output pixel (one im2col row) each -- straight from the uint8 crop:
+// a 256-entry lookup table maps a byte to the fp16 (hi, lo) pair of 16 * (u8 / 255) (exact IEEE divide on the host of
+// the kernel, so the fused path is bit-identical to the reference's float feed), and the row is written in the
+// 128-byte-swizzle K-major canonical layout.  K is padded to 80 = 5 MMA K-steps.  The packed weights ([128][128] K-major,
+// zero beyond k = 75) are TMA-loaded once per CTA and stay resident.  Persistent CTAs loop over 128-pixel tiles with a
+// 2-stage A ring and a double-buffered TMEM accumulator: builders (warps 0-3), epilogue (warps 4-7) and the MMA issuer
+// (warp 8) all overlap.  The epilogue writes conv2's input directly: (hi, lo) fp16, space-to-depth layout.
+#include <algorithm>
+
+#include "tc.cuh"
+#include "tc_common.cuh"
+
+namespace aae {
+
+using namespace tc;
+
+namespace {
+
+constexpr int C1_ATOM = 128 * 128;                 // 128 rows x 128 B
+constexpr int C1_STAGE = 4 * C1_ATOM;              // hi k[0,64), hi k[64,128), lo k[0,64), lo k[64,128)
+constexpr int C1_STAGES = 2;
+constexpr int C1_KPAD = 80;
+
+struct Conv1Params {
+  const void* x;           // crops NHWC, uint8 or float32
+  int B, H, W, C;          // input dims (C <= 3)
+  int OH, OW, N;           // output dims, N = Cout (<= 128)
+  int pad_t, pad_l;
+  int num_tiles;
+  const float* bias;
+  float unscale, out_scale, in_scale;
+  __half* out_hi;
+  __half* out_lo;
+};
+
+template <int N>
+struct Conv1Smem {
+  static constexpr int W_BYTES = 4 * N * 128;
+  static constexpr int TOTAL = W_BYTES + C1_STAGES * C1_STAGE + 1024 /*lut*/ + 1024 /*align*/ + 256;
+};
+
+template <bool U8>
+__device__ __forceinline__ uint32_t conv1_fetch(const Conv1Params& p, const uint32_t* lut, long long idx, bool ok) {
+  // returns (hi fp16 bits) | (lo fp16 bits << 16) of in_scale * pixel
+  if (!ok) return 0u;
+  if (U8) return lut[reinterpret_cast<const uint8_t*>(p.x)[idx]];
+  const float v = __ldg(reinterpret_cast<const float*>(p.x) + idx) * p.in_scale;
+  __half h, l;
+  split_f16(v, h, l);
+  return (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+}
+
+template <int N, int CIN, bool U8>
+__global__ void __launch_bounds__(288, 1)
+tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const Conv1Params p) {
+  using S = Conv1Smem<N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_smem = smem;                                   // hi k0, hi k1, lo k0, lo k1 (N rows x 128 B each)
+  uint8_t* a_smem = smem + S::W_BYTES;
+  uint32_t* lut = reinterpret_cast<uint32_t*>(a_smem + C1_STAGES * C1_STAGE);
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(lut + 256);
+  uint64_t* a_full = w_full + 1;
+  uint64_t* a_empty = a_full + C1_STAGES;
+  uint64_t* acc_full = a_empty + C1_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+
+  if (threadIdx.x < 256) {
+    // byte -> (hi, lo) of in_scale * (u8 / 255): the divide is the IEEE fp32 divide the reference's feed amounts to
+    const float v = ((float)threadIdx.x / 255.0f) * p.in_scale;
+    __half h, l;
+    split_f16(v, h, l);
+    lut[threadIdx.x] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+  }
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo);
+    mbar_init(w_full, 1);
+    for (int s = 0; s < C1_STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int hw = p.OH * p.OW;
+
+  if (warp < 4) {
+    // ===================== A builders: thread r owns im2col row r of the tile =====================
+    const int r = threadIdx.x;
+    constexpr int run = 5 * CIN;                             // contiguous bytes per kernel row (kw, c)
+    for (int i = 0; i < my_tiles; ++i) {
+      const int s = i % C1_STAGES;
+      const int m = ((int)blockIdx.x + i * (int)gridDim.x) * 128 + r;
+      const int b = m / hw, rem = m - b * hw, oh = rem / p.OW, ow = rem - oh * p.OW;
+      const int ih0 = oh * 2 - p.pad_t, iw0 = ow * 2 - p.pad_l;
+      const bool row_ok = b < p.B;
+      mbar_wait(&a_empty[s], ((uint32_t)(i / C1_STAGES) & 1u) ^ 1u);
+      uint8_t* st = a_smem + s * C1_STAGE;
+#pragma unroll
+      for (int ci = 0; ci < C1_KPAD / 8; ++ci) {             // one 16-byte chunk = 8 K elements
+        uint32_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = ci * 8 + j;
+          const int kh = k / run, jj = k - kh * run, kw = jj / CIN, c = jj - kw * CIN;
+          const int ih = ih0 + kh, iw = iw0 + kw;
+          const bool ok = row_ok && kh < 5 && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+          e[j] = conv1_fetch<U8>(p, lut, ((long long)(b * p.H + ih) * p.W + iw) * CIN + c, ok);
+        }
+        uint4 hv, lv;
+        hv.x = __byte_perm(e[0], e[1], 0x5410); lv.x = __byte_perm(e[0], e[1], 0x7632);
+        hv.y = __byte_perm(e[2], e[3], 0x5410); lv.y = __byte_perm(e[2], e[3], 0x7632);
+        hv.z = __byte_perm(e[4], e[5], 0x5410); lv.z = __byte_perm(e[4], e[5], 0x7632);
+        hv.w = __byte_perm(e[6], e[7], 0x5410); lv.w = __byte_perm(e[6], e[7], 0x7632);
+        const int atom = ci >> 3, chunk = ci & 7;
+        const uint32_t off = (uint32_t)(atom * C1_ATOM + r * 128 + ((chunk ^ (r & 7)) << 4));
+        *reinterpret_cast<uint4*>(st + off) = hv;
+        *reinterpret_cast<uint4*>(st + 2 * C1_ATOM + off) = lv;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[s]);
+    }
+  } else if (warp < 8) {
+    // ===================== epilogue =====================
+    const int q = warp & 3, r = q * 32 + lane;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int as = i & 1;
+      const int m = ((int)blockIdx.x + i * (int)gridDim.x) * 128 + r;
+      const int b = m / hw, rem = m - b * hw, oh = rem / p.OW, ow = rem - oh * p.OW;
+      const bool valid = b < p.B;
+      const long long row_off =
+          ((long long)(b * (p.OH >> 1) + (oh >> 1)) * (p.OW >> 1) + (ow >> 1)) * (4LL * p.N) + (((oh & 1) << 1) | (ow & 1)) * p.N;
+      mbar_wait(&acc_full[as], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + c * 32), v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a = fmaxf(__uint_as_float(v[j]) * p.unscale + __ldg(p.bias + c * 32 + j), 0.f) * p.out_scale;
+          float bb = fmaxf(__uint_as_float(v[j + 1]) * p.unscale + __ldg(p.bias + c * 32 + j + 1), 0.f) * p.out_scale;
+          __half ah, al, bh, bl;
+          split_f16(a, ah, al);
+          split_f16(bb, bh, bl);
+          hi[j >> 1] = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
+          lo[j >> 1] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+        }
+        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + row_off + c * 32);
+        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + row_off + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  } else {
+    // ===================== weight TMA + MMA issuer (warp 8) =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, S::W_BYTES);
+      tma_load_2d(w_smem, &tm_w_hi, w_full, 0, 0);
+      tma_load_2d(w_smem + N * 128, &tm_w_hi, w_full, 64, 0);
+      tma_load_2d(w_smem + 2 * N * 128, &tm_w_lo, w_full, 0, 0);
+      tma_load_2d(w_smem + 3 * N * 128, &tm_w_lo, w_full, 64, 0);
+      mbar_wait(w_full, 0);
+      constexpr uint32_t idesc = make_idesc_f16(128, N, 0);
+      const uint32_t wst = smem_u32(w_smem);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % C1_STAGES, as = i & 1;
+        mbar_wait(&acc_empty[as], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        mbar_wait(&a_full[s], (uint32_t)(i / C1_STAGES) & 1u);
+        tc_fence_after();
+        const uint32_t ast = smem_u32(a_smem + s * C1_STAGE);
+        const uint32_t d = tmem_base + (uint32_t)(as * N);
+#pragma unroll
+        for (int k = 0; k < C1_KPAD / 16; ++k) {
+          const int atom = k >> 2, kk = k & 3;
+          const uint64_t a_hi = desc_advance_k(make_sw128_kmajor_desc(ast + atom * C1_ATOM), kk);
+          const uint64_t a_lo = desc_advance_k(make_sw128_kmajor_desc(ast + (2 + atom) * C1_ATOM), kk);
+          const uint64_t w_hi = desc_advance_k(make_sw128_kmajor_desc(wst + atom * N * 128), kk);
+          const uint64_t w_lo = desc_advance_k(make_sw128_kmajor_desc(wst + (2 + atom) * N * 128), kk);
+          umma_f16(d, a_lo, w_hi, idesc, k > 0 ? 1u : 0u);
+          umma_f16(d, a_hi, w_lo, idesc, 1u);
+          umma_f16(d, a_hi, w_hi, idesc, 1u);
+        }
+        umma_commit(&a_empty[s]);
+        umma_commit(&acc_full[as]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// W fp32 [75][N] (HWIO flattened) -> (hi, lo) fp16 [N][128] K-major, scaled, zero for k >= K
+__global__ void pack_conv1_weights_kernel(const float* __restrict__ w, int K, int N, float scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 128) return;
+  const int n = i / 128, k = i - n * 128;
+  const float v = k < K ? w[(long long)k * N + n] * scale : 0.f;
+  __half h, l;
+  split_f16(v, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+
+}  // namespace
+
+struct TcConv1 {
+  int N, sm_count;
+  __half *w_hi = nullptr, *w_lo = nullptr;
+  CUtensorMap tm_hi, tm_lo;
+};
+
+bool tc_conv1_supported(const aae_net_cfg* cfg) {
+  const int oh = (cfg->in_h + 1) / 2, ow = (cfg->in_w + 1) / 2;
+  return cfg->kernel_size == 5 && cfg->strides[0] == 2 && cfg->in_c == 3 && cfg->filters[0] == 128 && (ow & (ow - 1)) == 0 &&
+         ow <= 128 && (128 % ow) == 0 && (oh % (128 / ow)) == 0 && (cfg->in_h % 2 == 0) && (cfg->in_w % 2 == 0);
+}
+
+int tc_conv1_create(int device, const aae_net_cfg* cfg, TcConv1** out) {
+  *out = nullptr;
+  TcConv1* h = new TcConv1();
+  h->N = cfg->filters[0];
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  h->sm_count = prop.multiProcessorCount;
+  cudaError_t e = cudaMalloc(&h->w_hi, (size_t)h->N * 128 * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMalloc(&h->w_lo, (size_t)h->N * 128 * sizeof(__half));
+  if (e != cudaSuccess) { set_error("tc conv1 alloc failed: %s", cudaGetErrorString(e)); tc_conv1_destroy(h); return AAE_ERR_OOM; }
+  const uint64_t dims[2] = {128, (uint64_t)h->N};
+  const uint64_t strides[1] = {256};
+  const uint32_t box[2] = {64, (uint32_t)h->N};
+  int st = make_tmap_f16(&h->tm_hi, h->w_hi, 2, dims, strides, box);
+  if (st == AAE_OK) st = make_tmap_f16(&h->tm_lo, h->w_lo, 2, dims, strides, box);
+  if (st != AAE_OK) { tc_conv1_destroy(h); return st; }
+  *out = h;
+  return AAE_OK;
+}
+
+void tc_conv1_destroy(TcConv1* h) {
+  if (!h) return;
+  cudaFree(h->w_hi); cudaFree(h->w_lo);
+  delete h;
+}
+
+int tc_conv1_pack(TcConv1* h, const float* w_dev, int K, float w_scale, cudaStream_t s) {
+  pack_conv1_weights_kernel<<<(unsigned)ceil_div(h->N * 128, 256), 256, 0, s>>>(w_dev, K, h->N, w_scale, h->w_hi, h->w_lo);
+  AAE_LAUNCH_OK();
+  return AAE_OK;
+}
+
+int tc_conv1_forward(TcConv1* h, const aae_net_cfg* cfg, const void* crops, int src_u8, int B, const float* bias, float act_scale,
+                     float w_scale, __half* out_hi, __half* out_lo, cudaStream_t s) {
+  Conv1Params p;
+  p.x = crops; p.B = B; p.H = cfg->in_h; p.W = cfg->in_w; p.C = cfg->in_c;
+  p.OH = cfg->in_h / 2; p.OW = cfg->in_w / 2; p.N = h->N;
+  p.pad_t = std::max((p.OH - 1) * 2 + 5 - p.H, 0) / 2;
+  p.pad_l = std::max((p.OW - 1) * 2 + 5 - p.W, 0) / 2;
+  p.num_tiles = (int)ceil_div((int64_t)B * p.OH * p.OW, 128);
+  p.bias = bias;
+  p.in_scale = act_scale; p.out_scale = act_scale; p.unscale = 1.f / (act_scale * w_scale);
+  p.out_hi = out_hi; p.out_lo = out_lo;
+  const int grid = std::min(h->sm_count, p.num_tiles);
+  using S = Conv1Smem<128>;
+  if (src_u8) {
+    AAE_CUDA_OK(cudaFuncSetAttribute(tc_conv1_kernel<128, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    tc_conv1_kernel<128, 3, true><<<grid, 288, S::TOTAL, s>>>(h->tm_hi, h->tm_lo, p);
+  } else {
+    AAE_CUDA_OK(cudaFuncSetAttribute(tc_conv1_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    tc_conv1_kernel<128, 3, false><<<grid, 288, S::TOTAL, s>>>(h->tm_hi, h->tm_lo, p);
+  }
+  AAE_LAUNCH_OK();
+  return AAE_OK;
+}
+
+}  // namespace aae

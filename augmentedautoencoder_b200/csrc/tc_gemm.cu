@@ -112,7 +112,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<N_TILE>(tmem_ptr);
+  if (warp == 2) tmem_alloc<2 * N_TILE>(tmem_ptr);   // [0,N) main hi*hi accumulator, [N,2N) cross-term accumulator
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -156,10 +156,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const uint64_t w_lo = make_sw128_kmajor_desc(st + 2 * S::A_BYTES + S::W_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          // small cross terms first, the dominant hi*hi product last
-          umma_f16(tmem_base, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, (i > 0 || k > 0) ? 1u : 0u);
-          umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
-          umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_hi, k), idesc, 1u);
+          // The tensor core truncates when it adds into a large fp32 accumulator, so the 2^-11-sized cross terms get an
+          // accumulator of their own (small magnitude -> negligible truncation) and are folded in by the epilogue in RN fp32.
+          const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
+          umma_f16(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_hi, k), idesc, first);
+          umma_f16(tmem_base + N_TILE, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, first);
+          umma_f16(tmem_base + N_TILE, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
       }
@@ -187,15 +189,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const bool has_work = it_end > it_begin;
 #pragma unroll 1
     for (int c = 0; c < N_TILE / 32; ++c) {
-      uint32_t v[32];
+      uint32_t v[32], x[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
       tmem_ld_wait();
       if (!valid) continue;
       const int n = n0 + c * 32;
       if (n >= p.N) continue;
       float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = has_work ? __uint_as_float(v[j]) * p.unscale : 0.f;
+      for (int j = 0; j < 32; ++j) f[j] = has_work ? (__uint_as_float(v[j]) + __uint_as_float(x[j])) * p.unscale : 0.f;
       if (p.out_mode == OUT_F32) {
         float* dst = p.out_f32 + (long long)blockIdx.z * p.M * p.N + row_off + n;
 #pragma unroll
@@ -228,7 +231,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<N_TILE>(tmem_base);
+    tmem_dealloc<2 * N_TILE>(tmem_base);
   }
 }
 
@@ -299,6 +302,7 @@ struct TcEncoder {
   int flat;
   float* partials = nullptr;     // dense split-K partials [splits, max_batch, latent]
   int dense_splits = 1;
+  TcConv1* conv1 = nullptr;      // tensor-core first layer (when the geometry allows), else the fp32 SIMT kernel
   float* dbg = nullptr;          // fp32 view of an activation (tests)
   size_t dbg_floats = 0;
   bool timer_on = false;
@@ -432,6 +436,7 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
     st = dev_alloc((void**)&h->partials, (size_t)h->dense_splits * (B + 128) * cfg->latent * sizeof(float));
     D.gp.out_f32 = h->partials;
   }
+  if (st == AAE_OK && tc_conv1_supported(cfg)) st = tc_conv1_create(device, cfg, &h->conv1);
   if (st != AAE_OK) { tc_encoder_destroy(h); return st; }
   *out = h;
   return AAE_OK;
@@ -442,12 +447,16 @@ void tc_encoder_destroy(TcEncoder* h) {
   for (auto& T : h->layers) { cudaFree(T.in_hi); cudaFree(T.in_lo); cudaFree(T.w_hi); cudaFree(T.w_lo); }
   cudaFree(h->partials);
   cudaFree(h->dbg);
+  tc_conv1_destroy(h->conv1);
   for (auto e : h->ev) cudaEventDestroy(e);
   delete h;
 }
 
 int tc_encoder_pack_weights(TcEncoder* h, int layer, const float* w_dev, cudaStream_t s) {
-  if (layer == 0) return AAE_OK;  // conv1 stays on the fp32 SIMT kernel (Cin = 3)
+  if (layer == 0) {
+    if (h->conv1) return tc_conv1_pack(h->conv1, w_dev, h->cfg.kernel_size * h->cfg.kernel_size * h->cfg.in_c, W_SCALE, s);
+    return AAE_OK;  // conv1 on the fp32 SIMT kernel
+  }
   AAE_REQUIRE(layer >= 1 && layer <= (int)h->layers.size(), "tc pack: layer %d out of range", layer);
   TcLayer& T = h->layers[layer - 1];
   dim3 grid((unsigned)ceil_div(T.out_c, 32), (unsigned)ceil_div(T.in_c, 32), (unsigned)T.taps), block(32, 8);
@@ -478,7 +487,9 @@ int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const
   const aae_net_cfg& cfg = h->cfg;
   h->ev_used = 0;
   tc_mark(h, s);
-  {  // conv1 (Cin = 3, K = 75): fp32 SIMT implicit GEMM, epilogue writes conv2's space-to-depth (hi, lo) input directly
+  if (h->conv1) {
+    AAE_TRY(tc_conv1_forward(h->conv1, &cfg, crops, src_u8, B, b0, ACT_SCALE, W_SCALE, h->layers[0].in_hi, h->layers[0].in_lo, s));
+  } else {  // conv1 (Cin = 3, K = 75): fp32 SIMT implicit GEMM, epilogue writes conv2's space-to-depth (hi, lo) input directly
     IGemmParams p;
     memset(&p, 0, sizeof(p));
     p.src = crops; p.src_u8 = src_u8;

@@ -78,30 +78,41 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_consta
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_ptr);
 
   // ---- prologue (all warps): l2-normalise, scale, split to (hi, lo) fp16, store 128B-swizzled K-major ----
-  for (int row = warp; row < MQ * 128; row += 8) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < B) v = __ldg(reinterpret_cast<const float4*>(z + (long long)row * 128) + lane);
-    float ss = v.x * v.x;
-    ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+  // 8 rows per warp in flight at once: the loads of a batch are issued before any of them is consumed
+  for (int rb = 0; rb < MQ * 128; rb += 64) {
+    float4 vv[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv = MT_SCALE / sqrtf(fmaxf(ss, 1e-12f));
-    const float x[4] = {v.x * inv, v.y * inv, v.z * inv, v.w * inv};
-    __half h[4], l[4];
+    for (int u = 0; u < 8; ++u) {
+      const int row = rb + u * 8 + warp;
+      vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < B) vv[u] = __ldg(reinterpret_cast<const float4*>(z + (long long)row * 128) + lane);
+    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split_f16(x[i], h[i], l[i]);
-    const int mq = row >> 7, r = row & 127;
-    const int khalf = lane >> 4;                         // k = 4*lane -> K-half
-    const int chunk = (lane & 15) >> 1;                  // 16-byte chunk inside the 128-byte row
-    const uint32_t off = (uint32_t)(khalf * MT_Q_HALF + r * 128 + ((chunk ^ (r & 7)) << 4) + ((lane & 1) << 3));
-    uint8_t* base = q_smem + mq * 4 * MT_Q_HALF;
-    uint2 hv, lv;
-    hv.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
-    hv.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
-    lv.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
-    lv.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
-    *reinterpret_cast<uint2*>(base + off) = hv;
-    *reinterpret_cast<uint2*>(base + 2 * MT_Q_HALF + off) = lv;
+    for (int u = 0; u < 8; ++u) {
+      const int row = rb + u * 8 + warp;
+      const float4 v = vv[u];
+      float ss = v.x * v.x;
+      ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = MT_SCALE / sqrtf(fmaxf(ss, 1e-12f));
+      const float x[4] = {v.x * inv, v.y * inv, v.z * inv, v.w * inv};
+      __half h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_f16(x[i], h[i], l[i]);
+      const int mq = row >> 7, r = row & 127;
+      const int khalf = lane >> 4;                         // k = 4*lane -> K-half
+      const int chunk = (lane & 15) >> 1;                  // 16-byte chunk inside the 128-byte row
+      const uint32_t off = (uint32_t)(khalf * MT_Q_HALF + r * 128 + ((chunk ^ (r & 7)) << 4) + ((lane & 1) << 3));
+      uint8_t* base = q_smem + mq * 4 * MT_Q_HALF;
+      uint2 hv, lv;
+      hv.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+      hv.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+      lv.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+      lv.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+      *reinterpret_cast<uint2*>(base + off) = hv;
+      *reinterpret_cast<uint2*>(base + 2 * MT_Q_HALF + off) = lv;
+    }
   }
   fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
   tc_fence_before();
