@@ -1,0 +1,115 @@
+"""CPU tests of the product's host-side logic against the golden vectors produced by the reference's own code
+(tests/golden/make_golden.py): view-sphere table, pose lift, crop extraction, checkpoint round trip, session shim."""
+import os
+
+import numpy as np
+import pytest
+
+from augmentedautoencoder_b200.ae import utils
+from augmentedautoencoder_b200.ae.codebook import lift_pose
+from augmentedautoencoder_b200.ae.dataset import Dataset
+
+
+def g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_viewsphere_matches_reference(golden_dir):
+    small = Dataset(None, min_n_views=162, num_cyclo=12, radius=700)
+    assert np.array_equal(small.viewsphere_for_embedding, g(golden_dir, "viewsphere_162x12.npz")["R"])
+    full = Dataset(None, min_n_views=2562, num_cyclo=36, radius=700)
+    ref = g(golden_dir, "viewsphere_2562x36.npz")
+    R = full.viewsphere_for_embedding
+    assert full.embedding_size == 92232
+    assert np.array_equal(R[::36], ref["view_R"]) and np.array_equal(R[:72], ref["first_rows"])
+    assert np.array_equal(R[-36:], ref["last_rows"]) and np.array_equal(R[ref["probe_idx"]], ref["probe_R"])
+
+
+def test_lift_pose_matches_reference(golden_dir):
+    p = g(golden_dir, "pose_lift.npz")
+    rs = Dataset(None, min_n_views=2562, num_cyclo=36, radius=700).viewsphere_for_embedding
+    for i in range(3):
+        idcs = np.atleast_1d(p[f"c{i}_idcs"])
+        table = np.zeros((92232, 4), dtype=np.int32)
+        table[idcs] = p[f"c{i}_bbs_at_idcs"]
+        r, t = lift_pose(idcs, rs, table, p[f"c{i}_bb"], p["k_test"], p["k_train"], float(p["radius"]))
+        assert np.array_equal(r, p[f"c{i}_Rs"]) and np.array_equal(t, p[f"c{i}_ts"])
+    table = np.zeros((92232, 4), dtype=np.int32)
+    table[int(p["depth_idx"][0])] = p["depth_bb"]
+    r, t = lift_pose(p["depth_idx"], rs, table, p["c2_bb"], p["k_test"], p["k_train"], float(p["radius"]), depth_pred=812.5)
+    assert np.array_equal(r, p["depth_Rs"]) and np.array_equal(t, p["depth_ts"])
+
+
+def test_square_patches_match_reference(golden_dir):
+    import cv2
+    from augmentedautoencoder_b200.m3_interface.ae_pose_estimator import AePoseEstimator
+    c = g(golden_dir, "crops_process.npz")
+    scene = np.random.RandomState(int(c["scene_seed"])).randint(0, 256, size=tuple(c["scene_shape"]), dtype=np.uint8)
+    est = AePoseEstimator.__new__(AePoseEstimator)
+    for b, want in zip(c["boxes"], c["crops_black_borders_linear"]):
+        got = est.extract_square_patch(scene, b, 1.2, resize=(128, 128), interpolation=cv2.INTER_LINEAR, black_borders=True)
+        assert np.array_equal(got, want)
+    ds = Dataset(None)
+    for b, want in zip(c["boxes"], c["crops_dataset_nearest"]):
+        assert np.array_equal(ds.extract_square_patch(scene, b, 1.2, resize=(128, 128), interpolation=cv2.INTER_NEAREST), want)
+
+
+def test_workspace_paths_and_batches():
+    assert utils.get_log_dir("/w", "exp", "grp") == "/w/experiments/grp/exp"
+    assert utils.get_checkpoint_dir("/w/experiments/grp/exp") == "/w/experiments/grp/exp/checkpoints"
+    assert utils.get_train_config_exp_file_path("/l", "exp") == "/l/exp.cfg"
+    assert list(utils.batch_iteration_indices(10, 4)) == [(0, 4), (4, 8), (8, 10)]
+    assert list(utils.batch_iteration_indices(8, 4)) == [(0, 4), (4, 8)]
+
+
+def test_variable_scope_names_follow_the_reference():
+    from augmentedautoencoder_b200 import _lib
+    from augmentedautoencoder_b200.ae import session as S
+    from augmentedautoencoder_b200.ae.encoder import Encoder
+    _lib.lib()
+    with S.variable_scope("obj_05"):
+        x = S.placeholder(np.float32, [None, 128, 128, 3])
+        enc = Encoder(x, 128, [128, 256, 512, 512], 5, [2, 2, 2, 2], False)
+    names = enc.variable_names
+    assert names[0] == "obj_05/conv2d/kernel" and names[2] == "obj_05/conv2d_1/kernel" and names[-2:] == ["obj_05/dense/kernel", "obj_05/dense/bias"]
+    w = enc.get_weights()
+    assert w["obj_05/conv2d/kernel"].shape == (5, 5, 3, 128) and w["obj_05/dense/kernel"].shape == (32768, 128)
+    assert np.all(w["obj_05/conv2d/bias"] == 0)                      # tf.layers default: zero bias, glorot-uniform kernel
+    lim = np.sqrt(6.0 / (25 * 3 + 25 * 128))
+    assert np.abs(w["obj_05/conv2d/kernel"]).max() <= lim
+    enc.load_weights({"conv2d_3/bias": np.ones(512, np.float32)})   # short names are accepted
+    assert np.all(enc.get_weights()["obj_05/conv2d_3/bias"] == 1)
+    with pytest.raises(ValueError):
+        enc.load_weights({"dense/kernel": np.zeros((3, 3), np.float32)})
+    with pytest.raises(NotImplementedError):
+        Encoder(x, 128, [128], 5, [2], True)
+
+
+def test_saver_round_trip(tmp_path):
+    from augmentedautoencoder_b200 import _lib
+    from augmentedautoencoder_b200.ae import factory
+    from augmentedautoencoder_b200.ae import session as S
+    from augmentedautoencoder_b200.ae.codebook import Codebook
+    from augmentedautoencoder_b200.ae.encoder import Encoder
+    _lib.lib()
+    ds = Dataset(None, min_n_views=162, num_cyclo=12, radius=700)
+    with S.variable_scope("e1"):
+        x = S.placeholder(np.float32, [None, 32, 32, 3])
+        enc = Encoder(x, 16, [8, 16], 5, [2, 2], False, seed=1)
+        cb = Codebook(enc, ds, True)
+    E = np.random.RandomState(0).randn(ds.embedding_size, 16).astype(np.float32)
+    cb.embedding_normalized.assign(E)
+    saver = factory.Saver([enc, cb])
+    path = saver.save(None, str(tmp_path / "checkpoints" / "chkpt"), global_step=30000)
+    assert path.endswith("chkpt-30000.npz")
+    with S.variable_scope("e1"):
+        enc2 = Encoder(S.placeholder(np.float32, [None, 32, 32, 3]), 16, [8, 16], 5, [2, 2], False, seed=2)
+        cb2 = Codebook(enc2, ds, True)
+    assert not np.array_equal(enc2.get_weights()["e1/conv2d/kernel"], enc.get_weights()["e1/conv2d/kernel"])
+    got = factory.restore_checkpoint(None, factory.Saver([enc2, cb2]), str(tmp_path / "checkpoints"))
+    assert got == path
+    for k, v in enc.get_weights().items():
+        assert np.array_equal(enc2.get_weights()[k], v)
+    assert np.array_equal(cb2.embedding_normalized.value(), E)
+    with pytest.raises(FileNotFoundError):
+        factory.restore_checkpoint(None, factory.Saver([enc2]), str(tmp_path / "nothing"))
