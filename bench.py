@@ -294,7 +294,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("AAE_BENCH_PRECISION", "simt"), choices=["simt", "tc"])
+    ap.add_argument("--precision", default=os.environ.get("AAE_BENCH_PRECISION", "tc"), choices=["simt", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -316,6 +316,40 @@ def ae_forward_loss(x: np.ndarray, target: np.ndarray, enc: Dict[str, np.ndarray
     return float(loss.item()), rec.detach().numpy(), grads
 
 
+def relu_margin(x: np.ndarray, enc: Dict[str, np.ndarray], dec: Dict[str, np.ndarray]) -> float:
+    """Smallest |pre-activation| over every ReLU unit of encoder + decoder, in float64.  A unit closer to zero than fp32
+    rounding can land on either side of the ReLU in any fp32 implementation (TF included), which changes its gradient
+    path discretely; gradient parity tests pick inputs whose margin is comfortably above that."""
+    dt = torch.float64
+    tp = {k: _t(v, dt) for k, v in {**enc, **dec}.items()}
+    n_enc = sum(1 for k in enc if k.startswith("conv2d") and k.endswith("kernel"))
+    strides = STRIDES[:n_enc]
+    m = float("inf")
+    with torch.no_grad():
+        h = _t(x, dt)
+        for i, s_ in enumerate(strides):
+            name = "conv2d" if i == 0 else f"conv2d_{i}"
+            pre = conv2d_same(h, tp[f"{name}/kernel"], tp[f"{name}/bias"], s_, None)
+            m = min(m, float(pre.abs().min()))
+            h = torch.relu(pre)
+        z = h.reshape(h.shape[0], -1) @ tp["dense/kernel"] + tp["dense/bias"]
+        pre = z @ tp["dense_1/kernel"] + tp["dense_1/bias"]
+        m = min(m, float(pre.abs().min()))
+        st = list(reversed(strides))
+        hw = x.shape[1]
+        dims = [int(hw / np.prod(st[i:])) for i in range(len(st))]
+        nf0 = tp["dense_1/kernel"].shape[1] // (dims[0] * dims[0])
+        h = torch.relu(pre).reshape(-1, dims[0], dims[0], nf0)
+        k = n_enc
+        for d in dims[1:]:
+            h = resize_nearest_2x(h, (d, d))
+            pre = conv2d_same(h, tp[f"conv2d_{k}/kernel"], tp[f"conv2d_{k}/bias"], 1, None)
+            m = min(m, float(pre.abs().min()))
+            h = torch.relu(pre)
+            k += 1
+    return m
+
+
 def tf_adam_step(p: np.ndarray, g: np.ndarray, m: np.ndarray, v: np.ndarray, t: int, lr: float = 2e-4,
                  beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8):
     """tf.train.AdamOptimizer update (auto_pose/ae/ae_factory.py:86-88):
