@@ -165,6 +165,16 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Same for the 64-byte-swizzle layout: rows of 32 fp16 (64 B), 8-row groups 512 B apart, CU_TENSOR_MAP_SWIZZLE_64B (layout type 4).
+__device__ __forceinline__ uint64_t make_sw64_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
 // Advance along K inside the 128-byte swizzle atom: +32 bytes (16 fp16) per UMMA_K step.
 __device__ __forceinline__ uint64_t desc_advance_k(uint64_t desc, int k_step) { return desc + (uint64_t)((k_step * 32) >> 4); }
 
@@ -200,6 +210,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_tmapEncodeTiled get_tmap_encoder();
 // fp16 tensor, `rank` dims (innermost first), 128-byte swizzle, zero fill out of bounds
-int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                  int swizzle_bytes = 128);
 
 }  // namespace aae

@@ -17,6 +17,8 @@
 //
 // Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
 // (TMEM -> registers -> bias/ReLU -> hi/lo split -> global, in the next layer's space-to-depth layout).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -39,7 +41,8 @@ PFN_tmapEncodeTiled get_tmap_encoder() {
   return fn;
 }
 
-int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                  int swizzle_bytes) {
   PFN_tmapEncodeTiled enc = get_tmap_encoder();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return AAE_ERR_CUDA; }
   cuuint64_t gdim[5], gstr[4];
@@ -47,7 +50,8 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return AAE_ERR_CUDA; }
   return AAE_OK;
@@ -76,19 +80,19 @@ struct TcGemmParams {
   float* out_f32;        // OUT_F32: [splits, M, N]
 };
 
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, int KCH = 64>
 struct TcSmem {
-  static constexpr int A_BYTES = 128 * 128;            // 128 rows x 64 fp16
-  static constexpr int W_BYTES = N_TILE * 128;
+  static constexpr int A_BYTES = 128 * KCH * 2;        // 128 rows x KCH fp16
+  static constexpr int W_BYTES = N_TILE * KCH * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, int KCH>
 __global__ void __launch_bounds__(256, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const TcGemmParams p) {
-  using S = TcSmem<N_TILE, STAGES>;
+  using S = TcSmem<N_TILE, STAGES, KCH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
@@ -131,11 +135,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int tap = it / p.chunks_per_tap, cc = it - tap * p.chunks_per_tap;
         uint8_t* st = smem + s * S::STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        const int c0 = p.tap_ch[tap] + cc * 64;
+        const int c0 = p.tap_ch[tap] + cc * KCH;
         const int x = ow0 + p.tap_dj[tap], y = oh0 + p.tap_di[tap];
         tma_load_4d(st, &tm_a_hi, &full_bar[s], c0, x, y, b0);
         tma_load_4d(st + S::A_BYTES, &tm_a_lo, &full_bar[s], c0, x, y, b0);
-        const int kcol = it * 64;
+        const int kcol = it * KCH;
         tma_load_2d(st + 2 * S::A_BYTES, &tm_w_hi, &full_bar[s], kcol, n0);
         tma_load_2d(st + 2 * S::A_BYTES + S::W_BYTES, &tm_w_lo, &full_bar[s], kcol, n0);
       }
@@ -150,12 +154,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint64_t a_hi = make_sw128_kmajor_desc(st);
-        const uint64_t a_lo = make_sw128_kmajor_desc(st + S::A_BYTES);
-        const uint64_t w_hi = make_sw128_kmajor_desc(st + 2 * S::A_BYTES);
-        const uint64_t w_lo = make_sw128_kmajor_desc(st + 2 * S::A_BYTES + S::W_BYTES);
+        const uint64_t a_hi = KCH == 64 ? make_sw128_kmajor_desc(st) : make_sw64_kmajor_desc(st);
+        const uint64_t a_lo = KCH == 64 ? make_sw128_kmajor_desc(st + S::A_BYTES) : make_sw64_kmajor_desc(st + S::A_BYTES);
+        const uint64_t w_hi = KCH == 64 ? make_sw128_kmajor_desc(st + 2 * S::A_BYTES) : make_sw64_kmajor_desc(st + 2 * S::A_BYTES);
+        const uint64_t w_lo = KCH == 64 ? make_sw128_kmajor_desc(st + 2 * S::A_BYTES + S::W_BYTES) : make_sw64_kmajor_desc(st + 2 * S::A_BYTES + S::W_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < KCH / 16; ++k) {
           // The tensor core truncates when it adds into a large fp32 accumulator, so the 2^-11-sized cross terms get an
           // accumulator of their own (small magnitude -> negligible truncation) and are folded in by the epilogue in RN fp32.
           const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
@@ -282,7 +286,6 @@ __global__ void unpack_act_kernel(const __half* __restrict__ hi, const __half* _
 // ------------------------------------------------------------------------------------------------- encoder plan
 constexpr float ACT_SCALE = 16.f;     // activations (and the [0,1] input) are stored as 16 * x
 constexpr float W_SCALE = 256.f;      // weights are stored as 256 * w
-constexpr int TC_N_TILE = 256;
 constexpr int TC_STAGES = 2;
 
 struct TcLayer {
@@ -293,6 +296,7 @@ struct TcLayer {
   CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo;
   TcGemmParams gp;
   int n_tile;
+  int kch;    // K chunk per pipeline stage: 64 (128-byte swizzle) or 32 (64-byte swizzle, 4 stages)
 };
 
 struct TcEncoder {
@@ -312,10 +316,10 @@ struct TcEncoder {
 
 namespace {
 
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, int KCH>
 int launch_tc_gemm(const TcLayer& L, dim3 grid, cudaStream_t s) {
-  using S = TcSmem<N_TILE, STAGES>;
-  auto kern = tc_gemm_kernel<N_TILE, STAGES>;
+  using S = TcSmem<N_TILE, STAGES, KCH>;
+  auto kern = tc_gemm_kernel<N_TILE, STAGES, KCH>;
   AAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   kern<<<grid, 256, S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w_hi, L.tm_w_lo, L.gp);
   AAE_LAUNCH_OK();
@@ -369,6 +373,7 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
       if (T.in_c % 64 != 0 || T.out_c % 32 != 0) { set_error("AAE_PREC_TC_SPLIT: dense layer needs flat %% 64 == 0 and latent %% 32 == 0"); st = AAE_ERR_UNSUPPORTED; break; }
     }
     T.n_tile = T.out_c >= 256 ? 256 : 128;
+    T.kch = (T.n_tile == 256 && getenv("AAE_TC_KCH64") == nullptr) ? 32 : 64;
     // batch dimension padded to a whole number of TMA boxes, so a tile never addresses rows outside the tensor map
     const int B_pad = (int)ceil_div(B, T.BB) * T.BB;
     const size_t act_alloc = (size_t)B_pad * T.in_h * T.in_w * T.in_c;
@@ -382,28 +387,28 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
       const uint64_t C4 = 4ull * T.in_c, W2 = T.in_w / 2, H2 = T.in_h / 2;
       const uint64_t dims[4] = {C4, W2, H2, (uint64_t)B_pad};
       const uint64_t strides[3] = {C4 * 2, W2 * C4 * 2, H2 * W2 * C4 * 2};
-      const uint32_t box[4] = {64, (uint32_t)T.BW, (uint32_t)T.BH, (uint32_t)T.BB};
-      if ((st = make_tmap_f16(&T.tm_a_hi, T.in_hi, 4, dims, strides, box)) != AAE_OK) break;
-      if ((st = make_tmap_f16(&T.tm_a_lo, T.in_lo, 4, dims, strides, box)) != AAE_OK) break;
+      const uint32_t box[4] = {(uint32_t)T.kch, (uint32_t)T.BW, (uint32_t)T.BH, (uint32_t)T.BB};
+      if ((st = make_tmap_f16(&T.tm_a_hi, T.in_hi, 4, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
+      if ((st = make_tmap_f16(&T.tm_a_lo, T.in_lo, 4, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
     } else {
       const uint64_t dims[4] = {(uint64_t)T.in_c, 1, 1, (uint64_t)B_pad};
       const uint64_t strides[3] = {(uint64_t)T.in_c * 2, (uint64_t)T.in_c * 2, (uint64_t)T.in_c * 2};
-      const uint32_t box[4] = {64, 1, 1, 128};
-      if ((st = make_tmap_f16(&T.tm_a_hi, T.in_hi, 4, dims, strides, box)) != AAE_OK) break;
-      if ((st = make_tmap_f16(&T.tm_a_lo, T.in_lo, 4, dims, strides, box)) != AAE_OK) break;
+      const uint32_t box[4] = {(uint32_t)T.kch, 1, 1, 128};
+      if ((st = make_tmap_f16(&T.tm_a_hi, T.in_hi, 4, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
+      if ((st = make_tmap_f16(&T.tm_a_lo, T.in_lo, 4, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
     }
     {
       const uint64_t K = (uint64_t)T.taps * T.in_c;
       const uint64_t dims[2] = {K, (uint64_t)T.out_c};
       const uint64_t strides[1] = {K * 2};
-      const uint32_t box[2] = {64, (uint32_t)std::min(T.n_tile, T.out_c)};
-      if ((st = make_tmap_f16(&T.tm_w_hi, T.w_hi, 2, dims, strides, box)) != AAE_OK) break;
-      if ((st = make_tmap_f16(&T.tm_w_lo, T.w_lo, 2, dims, strides, box)) != AAE_OK) break;
+      const uint32_t box[2] = {(uint32_t)T.kch, (uint32_t)std::min(T.n_tile, T.out_c)};
+      if ((st = make_tmap_f16(&T.tm_w_hi, T.w_hi, 2, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
+      if ((st = make_tmap_f16(&T.tm_w_lo, T.w_lo, 2, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
     }
     // ---- static GEMM parameters ----
     TcGemmParams& g = T.gp;
     g.N = T.out_c; g.OH = T.out_h; g.OW = T.out_w; g.BW = T.BW; g.BH = T.BH;
-    g.taps = T.taps; g.chunks_per_tap = T.in_c / 64;
+    g.taps = T.taps; g.chunks_per_tap = T.in_c / T.kch;
     g.iters_per_split = g.taps * g.chunks_per_tap;
     for (int t = 0; t < T.taps; ++t) {
       if (dense) { g.tap_di[t] = 0; g.tap_dj[t] = 0; g.tap_ch[t] = 0; continue; }
@@ -510,8 +515,9 @@ int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const
     const bool dense = (i + 1 == h->layers.size());
     T.gp.M = dense ? B : B * T.out_h * T.out_w;
     dim3 grid((unsigned)ceil_div(T.gp.M, 128), (unsigned)ceil_div(T.out_c, T.n_tile), dense ? (unsigned)h->dense_splits : 1u);
-    if (T.n_tile == 256) AAE_TRY((launch_tc_gemm<256, TC_STAGES>(T, grid, s)));
-    else AAE_TRY((launch_tc_gemm<128, 3>(T, grid, s)));
+    if (T.n_tile == 256 && T.kch == 32) AAE_TRY((launch_tc_gemm<256, 4, 32>(T, grid, s)));
+    else if (T.n_tile == 256) AAE_TRY((launch_tc_gemm<256, TC_STAGES, 64>(T, grid, s)));
+    else AAE_TRY((launch_tc_gemm<128, 3, 64>(T, grid, s)));
     if (dense) AAE_TRY(launch_splitk_reduce(h->partials, h->dense_splits, (int64_t)B * cfg.latent, cfg.latent, dense_b, ACT_NONE, z_out, s));
     tc_mark(h, s);
   }
