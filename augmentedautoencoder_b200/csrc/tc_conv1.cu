@@ -22,8 +22,11 @@ namespace {
 
 constexpr int C1_ATOM = 128 * 128;                 // 128 rows x 128 B
 constexpr int C1_STAGE = 4 * C1_ATOM;              // hi k[0,64), hi k[64,128), lo k[0,64), lo k[64,128)
-constexpr int C1_STAGES = 2;
+constexpr int C1_STAGES = 1;                       // the build (~0.4k cycles) is short next to the MMAs + epilogue; smem goes to the output staging
+constexpr int C1_OUT_LD = 1040;                    // staged output: 32 blocks of 1 KB (one space-to-depth position each), padded against bank conflicts
 constexpr int C1_KPAD = 80;
+constexpr int C1_PIX_ROWS = 7;                     // input rows feeding two output rows: 2*2 + 3
+constexpr int C1_PIX_LD = 400;                     // (128 + 3 padding pixels) * 3 channels = 393 words, rounded up
 
 struct Conv1Params {
   const void* x;           // crops NHWC, uint8 or float32
@@ -40,7 +43,9 @@ struct Conv1Params {
 template <int N>
 struct Conv1Smem {
   static constexpr int W_BYTES = 4 * N * 128;
-  static constexpr int TOTAL = W_BYTES + C1_STAGES * C1_STAGE + 1024 /*lut*/ + 1024 /*align*/ + 256;
+  static constexpr int PIX_BYTES = 2 * C1_PIX_ROWS * C1_PIX_LD * 4;   // double-buffered staged input rows, (hi|lo) words
+  static constexpr int OUT_BYTES = 2 * 32 * C1_OUT_LD;                // (hi, lo) output tile staged for bulk stores
+  static constexpr int TOTAL = W_BYTES + C1_STAGES * C1_STAGE + PIX_BYTES + OUT_BYTES + 1024 /*lut*/ + 1024 /*align*/ + 256;
 };
 
 template <bool U8>
@@ -62,16 +67,20 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* w_smem = smem;                                   // hi k0, hi k1, lo k0, lo k1 (N rows x 128 B each)
   uint8_t* a_smem = smem + S::W_BYTES;
-  uint32_t* lut = reinterpret_cast<uint32_t*>(a_smem + C1_STAGES * C1_STAGE);
+  uint32_t* pix = reinterpret_cast<uint32_t*>(a_smem + C1_STAGES * C1_STAGE);   // [2][C1_PIX_ROWS][C1_PIX_LD]
+  uint8_t* out_smem = reinterpret_cast<uint8_t*>(pix + 2 * C1_PIX_ROWS * C1_PIX_LD);   // [2 (hi,lo)][32][C1_OUT_LD]
+  uint32_t* lut = reinterpret_cast<uint32_t*>(out_smem + S::OUT_BYTES);
   uint64_t* w_full = reinterpret_cast<uint64_t*>(lut + 256);
   uint64_t* a_full = w_full + 1;
   uint64_t* a_empty = a_full + C1_STAGES;
   uint64_t* acc_full = a_empty + C1_STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  __shared__ float bias_s[N];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+  if (threadIdx.x < N) bias_s[threadIdx.x] = p.bias[threadIdx.x];
 
   if (threadIdx.x < 256) {
     // byte -> (hi, lo) of in_scale * (u8 / 255): the divide is the IEEE fp32 divide the reference's feed amounts to
@@ -80,6 +89,7 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
     split_f16(v, h, l);
     lut[threadIdx.x] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
   }
+  for (int i = threadIdx.x; i < 2 * C1_PIX_ROWS * C1_PIX_LD; i += blockDim.x) pix[i] = 0u;   // left/right padding pixels stay zero
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo);
     mbar_init(w_full, 1);
@@ -97,14 +107,71 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
 
   if (warp < 4) {
     // ===================== A builders: thread r owns im2col row r of the tile =====================
+    // Per tile (two output rows of one image) the 7 input rows it touches are first staged in shared memory with
+    // coalesced 16-byte loads and converted ONCE to packed (hi | lo << 16) fp16 words; each builder thread then
+    // assembles its 75-element patch from shared memory.  The raw rows of tile i+1 are fetched into registers before
+    // tile i is built, so the global-load latency hides behind the build.
     const int r = threadIdx.x;
-    constexpr int run = 5 * CIN;                             // contiguous bytes per kernel row (kw, c)
+    constexpr int run = 5 * CIN;                             // words per kernel row (kw, c)
+    constexpr int ROWW = 128 * CIN;                          // words per staged input row (image width 128)
+    constexpr int NV = U8 ? (C1_PIX_ROWS * ROWW / 16 + 127) / 128 : (C1_PIX_ROWS * ROWW / 4 + 127) / 128;
+    uint4 raw[NV];
+    auto fetch = [&](int tile) {                             // global -> registers
+      const int m_first = tile * 128;
+      const int b = m_first / hw, oh0 = (m_first - b * hw) / p.OW;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int u = r + v * 128;
+        raw[v] = make_uint4(0u, 0u, 0u, 0u);
+        if (U8) {
+          const int row = u / (ROWW / 16), c16 = u - row * (ROWW / 16);
+          const int ih = 2 * oh0 - p.pad_t + row;
+          if (row < C1_PIX_ROWS && b < p.B && ih >= 0 && ih < p.H)
+            raw[v] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + ((long long)(b * p.H + ih) * p.W) * CIN) + c16);
+        } else {
+          const int row = u / (ROWW / 4), c4 = u - row * (ROWW / 4);
+          const int ih = 2 * oh0 - p.pad_t + row;
+          if (row < C1_PIX_ROWS && b < p.B && ih >= 0 && ih < p.H)
+            raw[v] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.x) + ((long long)(b * p.H + ih) * p.W) * CIN) + c4);
+        }
+      }
+    };
+    auto stage = [&](uint32_t* dst) {                        // registers -> staged (hi|lo) words
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int u = r + v * 128;
+        if (U8) {
+          const int row = u / (ROWW / 16), c16 = u - row * (ROWW / 16);
+          if (row >= C1_PIX_ROWS) continue;
+          uint32_t* o = dst + row * C1_PIX_LD + p.pad_l * CIN + c16 * 16;
+          const uint32_t w4[4] = {raw[v].x, raw[v].y, raw[v].z, raw[v].w};
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = lut[(w4[j >> 2] >> ((j & 3) * 8)) & 0xFFu];
+        } else {
+          const int row = u / (ROWW / 4), c4 = u - row * (ROWW / 4);
+          if (row >= C1_PIX_ROWS) continue;
+          uint32_t* o = dst + row * C1_PIX_LD + p.pad_l * CIN + c4 * 4;
+          const float f4[4] = {__uint_as_float(raw[v].x), __uint_as_float(raw[v].y), __uint_as_float(raw[v].z), __uint_as_float(raw[v].w)};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __half h, l;
+            split_f16(f4[j] * p.in_scale, h, l);
+            o[j] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+          }
+        }
+      }
+    };
+    if (my_tiles > 0) {
+      fetch((int)blockIdx.x);
+      stage(pix);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int ow = r % p.OW, dr = r / p.OW;
     for (int i = 0; i < my_tiles; ++i) {
       const int s = i % C1_STAGES;
-      const int m = ((int)blockIdx.x + i * (int)gridDim.x) * 128 + r;
-      const int b = m / hw, rem = m - b * hw, oh = rem / p.OW, ow = rem - oh * p.OW;
-      const int ih0 = oh * 2 - p.pad_t, iw0 = ow * 2 - p.pad_l;
-      const bool row_ok = b < p.B;
+      const bool more = i + 1 < my_tiles;
+      if (more) fetch((int)blockIdx.x + (i + 1) * (int)gridDim.x);
+      const uint32_t* src = pix + (i & 1) * C1_PIX_ROWS * C1_PIX_LD + 2 * dr * C1_PIX_LD + 2 * ow * CIN;
       mbar_wait(&a_empty[s], ((uint32_t)(i / C1_STAGES) & 1u) ^ 1u);
       uint8_t* st = a_smem + s * C1_STAGE;
 #pragma unroll
@@ -113,10 +180,8 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int k = ci * 8 + j;
-          const int kh = k / run, jj = k - kh * run, kw = jj / CIN, c = jj - kw * CIN;
-          const int ih = ih0 + kh, iw = iw0 + kw;
-          const bool ok = row_ok && kh < 5 && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-          e[j] = conv1_fetch<U8>(p, lut, ((long long)(b * p.H + ih) * p.W + iw) * CIN + c, ok);
+          const int kh = k / run, jj = k - kh * run;
+          e[j] = kh < 5 ? src[kh * C1_PIX_LD + jj] : 0u;
         }
         uint4 hv, lv;
         hv.x = __byte_perm(e[0], e[1], 0x5410); lv.x = __byte_perm(e[0], e[1], 0x7632);
@@ -130,48 +195,60 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_full[s]);
+      if (more) stage(pix + ((i + 1) & 1) * C1_PIX_ROWS * C1_PIX_LD);
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // staged rows of tile i+1 visible; tile i's rows free for reuse
     }
   } else if (warp < 8) {
     // ===================== epilogue =====================
+    // The 128 pixels x 128 channels of a tile (two output rows of one image) are exactly ONE contiguous 32 KB slab of the
+    // consumer's space-to-depth tensor (row oh/2, all 32 column pairs, all four parities) -- per (hi, lo).  Each thread
+    // (= pixel) writes its 256 B into a padded shared-memory image of that slab; one thread then ships it with 1 KB bulk
+    // stores, i.e. full-line HBM writes instead of 16-byte scattered ones.
     const int q = warp & 3, r = q * 32 + lane;
+    const int ow = r % p.OW, dr = r / p.OW;
+    uint8_t* my_hi = out_smem + (ow >> 1) * C1_OUT_LD + (((dr & 1) << 1) | (ow & 1)) * (2 * N);
+    uint8_t* my_lo = my_hi + 32 * C1_OUT_LD;
     for (int i = 0; i < my_tiles; ++i) {
       const int as = i & 1;
-      const int m = ((int)blockIdx.x + i * (int)gridDim.x) * 128 + r;
-      const int b = m / hw, rem = m - b * hw, oh = rem / p.OW, ow = rem - oh * p.OW;
-      const bool valid = b < p.B;
-      const long long row_off =
-          ((long long)(b * (p.OH >> 1) + (oh >> 1)) * (p.OW >> 1) + (ow >> 1)) * (4LL * p.N) + (((oh & 1) << 1) | (ow & 1)) * p.N;
+      const int m_first = ((int)blockIdx.x + i * (int)gridDim.x) * 128;
+      const int b = m_first / hw, oh0 = (m_first - b * hw) / p.OW;
       mbar_wait(&acc_full[as], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
+      if (i > 0) {                                   // the previous tile's bulk stores must have finished reading the staging
+        if (warp == 4) bulk_wait_read_all();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
 #pragma unroll 1
       for (int c = 0; c < N / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + c * 32), v);
         tmem_ld_wait();
-        if (!valid) continue;
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float a = fmaxf(__uint_as_float(v[j]) * p.unscale + __ldg(p.bias + c * 32 + j), 0.f) * p.out_scale;
-          float bb = fmaxf(__uint_as_float(v[j + 1]) * p.unscale + __ldg(p.bias + c * 32 + j + 1), 0.f) * p.out_scale;
-          __half ah, al, bh, bl;
-          split_f16(a, ah, al);
-          split_f16(bb, bh, bl);
-          hi[j >> 1] = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
-          lo[j >> 1] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+          const float a = fmaxf(__uint_as_float(v[j]) * p.unscale + bias_s[c * 32 + j], 0.f) * p.out_scale;
+          const float bb = fmaxf(__uint_as_float(v[j + 1]) * p.unscale + bias_s[c * 32 + j + 1], 0.f) * p.out_scale;
+          split_f16x2(a, bb, hi[j >> 1], lo[j >> 1]);
         }
-        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + row_off + c * 32);
-        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + row_off + c * 32);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          *reinterpret_cast<uint4*>(my_hi + c * 64 + j * 16) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<uint4*>(my_lo + c * 64 + j * 16) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
+      fence_proxy_async_smem();                      // generic-proxy writes -> visible to the bulk-copy engine
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (warp == 4 && b < p.B) {                    // lane j ships 1 KB block j of the hi and of the lo slab
+        const long long slab = ((long long)(b * (p.OH >> 1) + (oh0 >> 1)) * (p.OW >> 1)) * (4LL * N);   // elements
+        bulk_store_1d(p.out_hi + slab + (long long)lane * 4 * N, out_smem + lane * C1_OUT_LD, 8 * N);
+        bulk_store_1d(p.out_lo + slab + (long long)lane * 4 * N, out_smem + (32 + lane) * C1_OUT_LD, 8 * N);
+        bulk_commit_group();
+      }
     }
+    if (warp == 4) bulk_wait_all();                    // all stores landed before the CTA exits
   } else {
     // ===================== weight TMA + MMA issuer (warp 8) =====================
     if (lane == 0) {
@@ -237,7 +314,7 @@ struct TcConv1 {
 bool tc_conv1_supported(const aae_net_cfg* cfg) {
   const int oh = (cfg->in_h + 1) / 2, ow = (cfg->in_w + 1) / 2;
   return cfg->kernel_size == 5 && cfg->strides[0] == 2 && cfg->in_c == 3 && cfg->filters[0] == 128 && (ow & (ow - 1)) == 0 &&
-         ow <= 128 && (128 % ow) == 0 && (oh % (128 / ow)) == 0 && (cfg->in_h % 2 == 0) && (cfg->in_w % 2 == 0);
+         ow == 64 && (oh % 2) == 0 && cfg->in_w == 128 && (cfg->in_h % 2 == 0);   // staging is laid out for 128-pixel-wide crops
 }
 
 int tc_conv1_create(int device, const aae_net_cfg* cfg, TcConv1** out) {

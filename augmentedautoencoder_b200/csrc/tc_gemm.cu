@@ -239,6 +239,149 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------- 2-CTA kernel
+// Same computation with CTA pairs (cta_group::2): two 128-pixel tiles that share a 256-channel weight tile run as ONE
+// M = 256 MMA.  Each CTA stages its own pixels plus only HALF of the weight tile (128 channels), so per K chunk it moves
+// 2/3 of the bytes of the single-CTA kernel through L2 -> smem and the tensor core reads 2/3 as much shared memory per
+// MMA -- the single-CTA version is shared-memory-bandwidth bound (operand reads + TMA writes > 128 B/clk/SM).  Both CTAs'
+// TMA loads complete on the leader's (even rank) barrier; the leader's issuer thread fires the MMAs and multicasts the
+// stage-free / accumulator-ready commits to both CTAs; each CTA drains its own 128 TMEM lanes.
+template <int STAGES, int KCH>
+struct TcSmem2 {
+  static constexpr int T_BYTES = 128 * KCH * 2;          // 128 rows x KCH fp16: A tile and W half tile have the same size
+  static constexpr int STAGE_BYTES = 4 * T_BYTES;        // A_hi, A_lo, W_hi(half), W_lo(half)
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int STAGES, int KCH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const TcGemmParams p) {
+  using S = TcSmem2<STAGES, KCH>;
+  constexpr int N_TILE = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m0 = blockIdx.x * 128;
+  const int n0 = blockIdx.y * N_TILE;
+  const int total_iters = p.taps * p.chunks_per_tap;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<512>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrival
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int hw = p.OH * p.OW;
+      const int b0 = m0 / hw, rem = m0 - b0 * hw;
+      const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], (((uint32_t)(it / STAGES)) & 1u) ^ 1u);
+        const int tap = it / p.chunks_per_tap, cc = it - tap * p.chunks_per_tap;
+        uint8_t* st = smem + s * S::STAGE_BYTES;
+        if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);   // bytes of both CTAs land on the leader's barrier
+        const uint32_t lb = leader_bar_addr(&full_bar[s]);
+        const int c0 = p.tap_ch[tap] + cc * KCH;
+        const int x = ow0 + p.tap_dj[tap], y = oh0 + p.tap_di[tap];
+        tma_load_4d_2sm(st, &tm_a_hi, lb, c0, x, y, b0);
+        tma_load_4d_2sm(st + S::T_BYTES, &tm_a_lo, lb, c0, x, y, b0);
+        const int kcol = it * KCH;
+        tma_load_2d_2sm(st + 2 * S::T_BYTES, &tm_w_hi, lb, kcol, n0 + (int)rank * 128);
+        tma_load_2d_2sm(st + 3 * S::T_BYTES, &tm_w_lo, lb, kcol, n0 + (int)rank * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, N_TILE, 0);
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], ((uint32_t)(it / STAGES)) & 1u);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint64_t a_hi = KCH == 64 ? make_sw128_kmajor_desc(st) : make_sw64_kmajor_desc(st);
+        const uint64_t a_lo = KCH == 64 ? make_sw128_kmajor_desc(st + S::T_BYTES) : make_sw64_kmajor_desc(st + S::T_BYTES);
+        const uint64_t w_hi = KCH == 64 ? make_sw128_kmajor_desc(st + 2 * S::T_BYTES) : make_sw64_kmajor_desc(st + 2 * S::T_BYTES);
+        const uint64_t w_lo = KCH == 64 ? make_sw128_kmajor_desc(st + 3 * S::T_BYTES) : make_sw64_kmajor_desc(st + 3 * S::T_BYTES);
+#pragma unroll
+        for (int k = 0; k < KCH / 16; ++k) {
+          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+          umma_f16_2sm(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_hi, k), idesc, first);
+          umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, first);
+          umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
+        }
+        umma_commit_2sm(&empty_bar[s]);
+      }
+      umma_commit_2sm(tmem_full_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int m = m0 + r;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool valid = m < p.M;
+    long long row_off = 0;
+    if (valid) {
+      if (p.out_mode == OUT_S2D_SPLIT) {
+        const int hw = p.OH * p.OW;
+        const int b = m / hw, rem = m - b * hw;
+        const int oh = rem / p.OW, ow = rem - oh * p.OW;
+        row_off = ((long long)(b * (p.OH >> 1) + (oh >> 1)) * (p.OW >> 1) + (ow >> 1)) * (4LL * p.N) + (((oh & 1) << 1) | (ow & 1)) * p.N;
+      } else {
+        row_off = (long long)m * p.N;
+      }
+    }
+#pragma unroll 1
+    for (int c = 0; c < N_TILE / 32; ++c) {
+      uint32_t v[32], x[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
+      tmem_ld_wait();
+      if (!valid) continue;
+      const int n = n0 + c * 32;
+      if (n >= p.N) continue;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float a = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * p.unscale + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+        float b = (__uint_as_float(v[j + 1]) + __uint_as_float(x[j + 1])) * p.unscale + (p.bias ? __ldg(p.bias + n + j + 1) : 0.f);
+        if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+        split_f16x2(a * p.out_scale, b * p.out_scale, hi[j >> 1], lo[j >> 1]);
+      }
+      uint4* dh = reinterpret_cast<uint4*>(p.out_hi + row_off + n);
+      uint4* dl = reinterpret_cast<uint4*>(p.out_lo + row_off + n);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still read this CTA's smem / signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- packing kernels
 namespace {
 
@@ -294,6 +437,8 @@ struct TcLayer {
   __half *in_hi = nullptr, *in_lo = nullptr;    // activations entering this layer
   __half *w_hi = nullptr, *w_lo = nullptr;      // packed weights [out_c][taps*in_c]
   CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo;
+  CUtensorMap tm_w2_hi, tm_w2_lo;               // weight tile halves (128 rows) for the CTA-pair kernel
+  bool pair = false;
   TcGemmParams gp;
   int n_tile;
   int kch;    // K chunk per pipeline stage: 64 (128-byte swizzle) or 32 (64-byte swizzle, 4 stages)
@@ -315,6 +460,17 @@ struct TcEncoder {
 };
 
 namespace {
+
+template <int STAGES, int KCH>
+int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
+  using S = TcSmem2<STAGES, KCH>;
+  auto kern = tc_gemm2_kernel<STAGES, KCH>;
+  AAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  grid.x = (grid.x + 1) & ~1u;   // whole CTA pairs
+  kern<<<grid, 256, S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w2_hi, L.tm_w2_lo, L.gp);
+  AAE_LAUNCH_OK();
+  return AAE_OK;
+}
 
 template <int N_TILE, int STAGES, int KCH>
 int launch_tc_gemm(const TcLayer& L, dim3 grid, cudaStream_t s) {
@@ -404,6 +560,12 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
       const uint32_t box[2] = {(uint32_t)T.kch, (uint32_t)std::min(T.n_tile, T.out_c)};
       if ((st = make_tmap_f16(&T.tm_w_hi, T.w_hi, 2, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
       if ((st = make_tmap_f16(&T.tm_w_lo, T.w_lo, 2, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
+      T.pair = !dense && T.n_tile == 256 && T.out_c % 256 == 0 && getenv("AAE_TC_1CTA") == nullptr;
+      if (T.pair) {
+        const uint32_t box2[2] = {(uint32_t)T.kch, 128};
+        if ((st = make_tmap_f16(&T.tm_w2_hi, T.w_hi, 2, dims, strides, box2, 2 * T.kch)) != AAE_OK) break;
+        if ((st = make_tmap_f16(&T.tm_w2_lo, T.w_lo, 2, dims, strides, box2, 2 * T.kch)) != AAE_OK) break;
+      }
     }
     // ---- static GEMM parameters ----
     TcGemmParams& g = T.gp;
@@ -515,7 +677,9 @@ int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const
     const bool dense = (i + 1 == h->layers.size());
     T.gp.M = dense ? B : B * T.out_h * T.out_w;
     dim3 grid((unsigned)ceil_div(T.gp.M, 128), (unsigned)ceil_div(T.out_c, T.n_tile), dense ? (unsigned)h->dense_splits : 1u);
-    if (T.n_tile == 256 && T.kch == 32) AAE_TRY((launch_tc_gemm<256, 4, 32>(T, grid, s)));
+    if (T.pair && T.kch == 32) AAE_TRY((launch_tc_gemm2<6, 32>(T, grid, s)));
+    else if (T.pair) AAE_TRY((launch_tc_gemm2<3, 64>(T, grid, s)));
+    else if (T.n_tile == 256 && T.kch == 32) AAE_TRY((launch_tc_gemm<256, 4, 32>(T, grid, s)));
     else if (T.n_tile == 256) AAE_TRY((launch_tc_gemm<256, TC_STAGES, 64>(T, grid, s)));
     else AAE_TRY((launch_tc_gemm<128, 3, 64>(T, grid, s)));
     if (dense) AAE_TRY(launch_splitk_reduce(h->partials, h->dense_splits, (int64_t)B * cfg.latent, cfg.latent, dense_b, ACT_NONE, z_out, s));
