@@ -37,6 +37,10 @@ LATENT = 128
 ENC_FLOP_PER_CROP = 2 * 2140667904
 LAYER_MAC_PER_CROP = [39321600, 838860800, 838860800, 419430400, 4194304]
 MATCH_BYTES = N_ROWS * LATENT * 4 + BATCH * LATENT * 4 + BATCH * 8
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures of this exact workload
+# (profiles/r01_ncu_*.txt; precision=tc, batch 256).  Algorithmic bytes beside them: conv2 = 537 MB (hi,lo) input + 3.3 MB
+# weights + 268 MB output = 808 MB; match = 47.36 MB.
+NCU_TRAFFIC = {"tc": {"conv1": 12688384 + 477692672, "conv2": 551194880 + 236450048, "match": 47414272 + 1536}}
 
 
 def peaks():
@@ -256,14 +260,18 @@ def run_ours(args, rank, world, local_rank):
         ach = flops / (stage_med[dom] * 1e-3) / 1e12
         peak = pk["tf_burst"]
         names = ["conv1 (3->128)", "conv2 (128->256)", "conv3 (256->512)", "conv4 (512->512)", "dense (32768->128)"]
+        products = 3 if args.precision == "tc" else 1
+        traffic = NCU_TRAFFIC.get(args.precision, {}).get(["conv1", "conv2", "conv3", "conv4", "dense"][dom])
         roof = {"kernel": "encoder " + names[dom], "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "peak_source": pk["src"] + " bf16 burst", "stage_ms": stage_med,
+                "traffic": traffic, "peak_source": pk["src"] + " bf16 burst", "stage_ms": stage_med,
+                "tensor_pipe": {"products_per_mac": products, "issued_tflops": ach * products, "issued_frac_of_peak": ach * products / peak,
+                                "why": "fp32-grade results need hi*hi + hi*lo + lo*hi on fp16 tensor cores; `achieved` counts each MAC once"},
                 "share_of_step": stage_med[dom] / ms_per_step,
                 "note": "algorithmic FLOPs (2*MAC) of the layer / cudaEvent duration; precision=%s" % args.precision}
     mm = statistics.median(match_ms) if match_ms else float("nan")
     ach_b = MATCH_BYTES / (mm * 1e-3) / 1e9
     roof_match = {"kernel": "fused codebook match (l2norm + scores + argmax)", "bound": "hbm", "achieved": ach_b, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                  "frac": ach_b / pk["hbm_gbs"], "traffic": None, "ms": mm, "bytes": MATCH_BYTES, "peak_source": pk["src"]}
+                  "frac": ach_b / pk["hbm_gbs"], "traffic": NCU_TRAFFIC.get(args.precision, {}).get("match"), "ms": mm, "bytes": MATCH_BYTES, "peak_source": pk["src"]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         q1, n1, t1 = cpu_reference_qps(12.0, batch=1)
@@ -288,6 +296,48 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_train(args, rank, world, local_rank):
+    """BASELINE.json configs[2]: AAE training step (encode + decode + bootstrapped L2 + backward + TF-Adam), batch 64, one GPU.
+    Not the headline metric: an extra line for the results table (python bench.py --workload train)."""
+    import torch
+    from augmentedautoencoder_b200 import _lib, build_ext
+    build_ext.build()
+    torch.cuda.set_device(local_rank)
+    from augmentedautoencoder_b200.ae.ae import AE
+    from augmentedautoencoder_b200.ae.ae_factory import TrainOp
+    from augmentedautoencoder_b200.ae.decoder import Decoder
+    from augmentedautoencoder_b200.ae.encoder import Encoder
+    from augmentedautoencoder_b200.ae.session import placeholder
+    B = 64
+    x = placeholder(np.float32, [None, 128, 128, 3])
+    y = placeholder(np.float32, [None, 128, 128, 3])
+    enc = Encoder(x, LATENT, [128, 256, 512, 512], 5, [2, 2, 2, 2], False, is_training=True, max_batch=B)
+    dec = Decoder(y, enc.z, [512, 512, 256, 128], 5, [2, 2, 2, 2], "L2", 4, False, False, is_training=True, max_batch=B)
+    top = TrainOp(AE(enc, dec, 0, 0), 2e-4)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    xb = torch.rand((B, 128, 128, 3), device="cuda", generator=g)
+    yb = torch.rand((B, 128, 128, 3), device="cuda", generator=g)
+    lib = _lib.lib()
+    for _ in range(max(args.warmup, 3)):
+        top.step_device(xb, yb)
+    torch.cuda.synchronize()
+    l0 = lib.aae_launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        loss = top.step_device(xb, yb)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / args.steps
+    flop = 3 * (4.2813e9 + 17.1002e9) * B
+    print(json.dumps({"metric": "AAE training steps/sec (batch 64, 128x128)", "value": 1e3 / ms, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "images_per_s": B * 1e3 / ms, "config": {"workload": "configs[2]: AAE training step, batch=64", "precision": "fp32 SIMT"},
+                      "gpu_launches": int(lib.aae_launch_count() - l0), "loss": float(loss),
+                      "roofline": {"bound": "fp32 FMA", "achieved": flop / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                   "note": "algorithmic 4.105 TFLOP per step (SURVEY 8d); CUDA-core fp32 path, not tensor cores yet"}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -296,12 +346,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("AAE_BENCH_PRECISION", "tc"), choices=["simt", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.workload == "train":
+        if rank == 0:
+            run_train(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)
