@@ -125,6 +125,35 @@ class Codebook(object):
             return idcs
         return self._dataset.viewsphere_for_embedding[idcs].squeeze()
 
+    def nearest_rotation_async(self, session, x, upright=False):
+        """Non-blocking variant for streaming callers: the host->device copy of `x` (ideally a pinned uint8 tensor) runs on
+        the session's copy stream, the encoder + fused match on the compute stream, and the [B] indices come back through a
+        pinned buffer.  Returns a ``PendingIndices``; ``.result()`` yields what ``nearest_rotation(..., return_idcs=True)``
+        would.  Issue call i+1 before collecting call i to overlap the PCIe copy with the previous batch's compute."""
+        dev = session.device
+        if not isinstance(x, torch.Tensor):
+            a = np.asarray(x)
+            x = torch.from_numpy(np.ascontiguousarray(a if a.dtype == np.uint8 else a.astype(np.float32)))
+        if x.ndim == 3:
+            x = x[None]
+        with torch.cuda.device(dev):
+            compute = torch.cuda.current_stream(dev)
+            copy = session.copy_stream
+            with torch.cuda.stream(copy):
+                xd = x.to(dev, non_blocking=True)
+                if xd.dtype != torch.uint8:
+                    xd = xd.to(torch.float32)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            xd.record_stream(compute)
+            compute.wait_event(ready)
+            _, idx = self.nearest_idx_device(xd.contiguous(), k=1, upright=upright)
+            host = torch.empty(idx.shape, dtype=torch.int32, pin_memory=True)
+            host.copy_(idx, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(compute)
+        return PendingIndices(host, done)
+
     def auto_pose6d(self, session, x, predicted_bb, K_test, top_n, train_args, depth_pred=None, upright=False):
         """Rotation from the codebook + translation from the bbox-diagonal ratio + rotation correction
         (auto_pose/ae/codebook.py:79-129)."""
@@ -182,6 +211,20 @@ class Codebook(object):
             self.close()
         except Exception:
             pass
+
+
+class PendingIndices:
+    """Handle returned by Codebook.nearest_rotation_async."""
+
+    def __init__(self, host_buf, event):
+        self._host, self._event = host_buf, event
+
+    def done(self):
+        return self._event.query()
+
+    def result(self):
+        self._event.synchronize()
+        return self._host.numpy().astype(np.int64)[:, 0]
 
 
 def lift_pose(idcs, rs_table, embed_obj_bbs, predicted_bb, K_test, K_train, render_radius, depth_pred=None):

@@ -115,6 +115,14 @@ class Session:
         if device is None:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self._copy_stream = None
+
+    @property
+    def copy_stream(self):
+        """Side stream for host<->device copies that overlap compute (Codebook.nearest_rotation_async)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        return self._copy_stream
 
     @property
     def stream_ptr(self):

@@ -1,4 +1,5 @@
 """Builds libaae_b200.so in-tree with nvcc for sm_100a (the only target: no multi-arch, no fallbacks)."""
+import hashlib
 import os
 import subprocess
 import sys
@@ -20,11 +21,25 @@ def _newest(paths):
     return max(os.path.getmtime(p) for p in paths)
 
 
+def _digest(paths):
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(os.path.basename(p).encode())
+        h.update(open(p, "rb").read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile (if needed) and return the path of libaae_b200.so.  Staleness is decided by a content hash of the sources
+    stored beside the library (file times do not survive every copy of the tree), and the library is replaced atomically
+    so that other ranks may dlopen it while rank 0 is (re)building."""
     srcs = sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + \
         [os.path.join(HERE, "..", "include", "aae_b200.h")]
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest(deps):
+    stamp = LIB + ".sha256"
+    digest = _digest(deps)
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -44,10 +59,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)
+    with open(stamp, "w") as f:
+        f.write(digest + "\n")
     return LIB
 
 

@@ -189,3 +189,17 @@ def test_update_embedding_builds_a_normalised_codebook(sess):
     assert np.array_equal(idc, np.arange(5))
     with pytest.raises(NotImplementedError):
         cb.update_embedding(sess, 16)                               # rendering needs a user-supplied renderer
+
+
+def test_async_streaming_call_matches_blocking_call(sess):
+    p = O.make_encoder_params(42)
+    E = O.make_codebook(7, n=36 * 300)
+    enc = _enc(1, 64, p)
+    cb = _codebook(enc, E, max_batch=64, precision=1)
+    batches = [torch.from_numpy(O.make_crops_u8(100 + i, 64)).pin_memory() for i in range(4)]
+    want = [cb.nearest_rotation(sess, b, return_idcs=True) for b in batches]
+    pend = [cb.nearest_rotation_async(sess, b) for b in batches]      # all four in flight
+    got = [h.result() for h in pend]
+    for w, g_ in zip(want, got):
+        assert g_.dtype == np.int64 and np.array_equal(w, g_)
+    assert np.array_equal(cb.nearest_rotation_async(sess, batches[0].numpy()).result(), want[0])   # pageable numpy input works too
