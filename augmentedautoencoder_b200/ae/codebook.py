@@ -148,11 +148,24 @@ class Codebook(object):
             xd.record_stream(compute)
             compute.wait_event(ready)
             _, idx = self.nearest_idx_device(xd.contiguous(), k=1, upright=upright)
-            host = torch.empty(idx.shape, dtype=torch.int32, pin_memory=True)
+            host = self._pinned_result(idx.shape)
             host.copy_(idx, non_blocking=True)
             done = torch.cuda.Event()
             done.record(compute)
         return PendingIndices(host, done)
+
+    def _pinned_result(self, shape, depth=8):
+        """Ring of pinned host buffers for the async read-back (cudaHostAlloc per call would cost more than the kernel)."""
+        ring = self.__dict__.setdefault("_pin_ring", {})
+        key = tuple(shape)
+        bufs, pos = ring.get(key, ([], 0))
+        if len(bufs) < depth:
+            bufs.append(torch.empty(key, dtype=torch.int32, pin_memory=True))
+            buf = bufs[-1]
+        else:
+            buf = bufs[pos % depth]
+        ring[key] = (bufs, pos + 1)
+        return buf
 
     def auto_pose6d(self, session, x, predicted_bb, K_test, top_n, train_args, depth_pred=None, upright=False):
         """Rotation from the codebook + translation from the bbox-diagonal ratio + rotation correction
@@ -224,7 +237,7 @@ class PendingIndices:
 
     def result(self):
         self._event.synchronize()
-        return self._host.numpy().astype(np.int64)[:, 0]
+        return self._host.numpy().astype(np.int64)[:, 0]   # astype copies: the pinned buffer goes back to the ring
 
 
 def lift_pose(idcs, rs_table, embed_obj_bbs, predicted_bb, K_test, K_train, render_radius, depth_pred=None):

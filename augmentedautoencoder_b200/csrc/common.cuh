@@ -94,6 +94,9 @@ struct IGemmParams {
   __half* split_lo;
   float split_scale;
   int split_s2d;
+  // depth-to-space output (FWD): C column n = (cls, co), cls = (py, px); row m = (b, i, j) on the PH x PW grid is written
+  // to pixel (2i+py, 2j+px) of a plain NHWC tensor [B, 2PH, 2PW, N/4]  (sub-pixel form of upsample-x2 + conv5x5)
+  int d2s_out;
 };
 
 int launch_igemm(const IGemmParams& p, int mode, cudaStream_t stream);
@@ -109,6 +112,14 @@ int launch_mul_mask(float* dy, const float* y, int64_t n, cudaStream_t stream); 
 int launch_sigmoid_grad(float* dx, const float* x, int64_t n, cudaStream_t stream);          // dx *= x (1 - x)
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
                 cudaStream_t stream);
+// Sub-pixel form of "nearest-neighbour x2 upsample, then conv 5x5 stride 1 SAME" (auto_pose/ae/decoder.py:54-62): the four
+// output parities (py, px) are four 3x3 convolutions of the LOW-resolution input whose taps are sums of the original
+// taps that land on the same source pixel -- 9/25 of the multiply-adds.  W [5,5,ci,co] -> Wm [3,3,ci,(py,px,co)].
+int launch_merge_subpixel_weights(const float* w, int cin, int cout, float* wm, cudaStream_t stream);
+// gradient wrt the original taps: dW[kh,kw] = sum over the parities of the merged tap it was folded into
+int launch_unmerge_subpixel_grads(const float* dwm, int cin, int cout, float* dw, cudaStream_t stream);
+// plain NHWC [B, 2h, 2w, C] -> space-to-depth [B, h, w, (py, px, c)]
+int launch_space_to_depth(const float* in, float* out, int B, int h, int w, int C, cudaStream_t stream);
 int launch_conv_small_n(const IGemmParams& p, cudaStream_t stream);
 // p.K = number of pixels, p.Bm = dY [pixels, N<=3]; partial: [chunks, taps*SC*N]
 int launch_wgrad_small_n(const IGemmParams& p, int chunks, float* partial, cudaStream_t stream);

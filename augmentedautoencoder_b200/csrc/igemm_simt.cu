@@ -301,6 +301,11 @@ __global__ void __launch_bounds__(NT) igemm_f32_kernel(const IGemmParams p) {
         lv.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
         *reinterpret_cast<uint2*>(p.split_hi + o) = hv;
         *reinterpret_cast<uint2*>(p.split_lo + o) = lv;
+      } else if (MODE == GATHER_FWD && p.d2s_out && !split) {
+        const PixCoord pc = decode_pixel(p, m, p.M);
+        const int co_n = p.N >> 2, cls = n / co_n, co = n - cls * co_n;
+        const long long o = ((long long)(pc.n * 2 * p.PH + 2 * pc.ph + (cls >> 1)) * (2 * p.PW) + 2 * pc.pw + (cls & 1)) * co_n + co;
+        *reinterpret_cast<float4*>(p.C + o) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
         *reinterpret_cast<float4*>(cbase + row * p.N + n) = make_float4(v[0], v[1], v[2], v[3]);
       }

@@ -162,6 +162,59 @@ __global__ void wgrad_small_n_kernel(const IGemmParams p, int pix_per_chunk, flo
   for (int c = 0; c < CO; ++c) o[c] = acc[c];
 }
 
+// which merged tap (0..2) original tap k (0..4) folds into for output parity p: source pixel offset floor((p + k - 2) / 2) + 1
+__device__ __forceinline__ int subpixel_tap(int parity, int k) { return ((parity + k - 2 + 4) >> 1) - 2 + 1; }
+
+__global__ void merge_subpixel_weights_kernel(const float* __restrict__ w, int cin, int cout, float* __restrict__ wm) {
+  // one thread per (dy, dx, ci, cls, co)
+  const long long total = 9LL * cin * 4 * cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout);
+    long long r = i / cout;
+    const int cls = (int)(r % 4); r /= 4;
+    const int ci = (int)(r % cin); r /= cin;
+    const int dx = (int)(r % 3), dy = (int)(r / 3);
+    const int py = cls >> 1, px = cls & 1;
+    float s = 0.f;
+    for (int kh = 0; kh < 5; ++kh) {
+      if (subpixel_tap(py, kh) != dy) continue;
+      for (int kw = 0; kw < 5; ++kw)
+        if (subpixel_tap(px, kw) == dx) s += w[((long long)(kh * 5 + kw) * cin + ci) * cout + co];
+    }
+    wm[i] = s;
+  }
+}
+
+__global__ void unmerge_subpixel_grads_kernel(const float* __restrict__ dwm, int cin, int cout, float* __restrict__ dw) {
+  const long long total = 25LL * cin * cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout);
+    long long r = i / cout;
+    const int ci = (int)(r % cin);
+    const int tap = (int)(r / cin), kh = tap / 5, kw = tap - kh * 5;
+    float s = 0.f;
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls) {
+      const int dy = subpixel_tap(cls >> 1, kh), dx = subpixel_tap(cls & 1, kw);
+      s += dwm[(((long long)(dy * 3 + dx) * cin + ci) * 4 + cls) * cout + co];
+    }
+    dw[i] = s;
+  }
+}
+
+__global__ void space_to_depth_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int h, int w, int C4) {
+  const long long total = (long long)B * h * w * 4 * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long r = i / C4;
+    const int cls = (int)(r % 4); r /= 4;
+    const int j = (int)(r % w); r /= w;
+    const int ii = (int)(r % h);
+    const int b = (int)(r / h);
+    out[i] = in[(((long long)b * 2 * h + 2 * ii + (cls >> 1)) * (2 * w) + 2 * j + (cls & 1)) * C4 + c];
+  }
+}
+
 __global__ void l2_normalize_kernel(const float* __restrict__ z, int B, int J, float* __restrict__ out) {
   // one warp per row; tf.nn.l2_normalize: z * rsqrt(max(sum z^2, 1e-12))  (auto_pose/ae/codebook.py:27)
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -227,6 +280,26 @@ int launch_sigmoid_grad(float* dx, const float* x, int64_t n, cudaStream_t strea
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
                 cudaStream_t stream) {
   adam_kernel<<<grid_for(n, 256), 256, 0, stream>>>(p, g, m, v, n, lr_t, b1, b2, eps);
+  AAE_LAUNCH_OK();
+  return AAE_OK;
+}
+
+int launch_merge_subpixel_weights(const float* w, int cin, int cout, float* wm, cudaStream_t stream) {
+  merge_subpixel_weights_kernel<<<grid_for(9LL * cin * 4 * cout, 256), 256, 0, stream>>>(w, cin, cout, wm);
+  AAE_LAUNCH_OK();
+  return AAE_OK;
+}
+
+int launch_unmerge_subpixel_grads(const float* dwm, int cin, int cout, float* dw, cudaStream_t stream) {
+  unmerge_subpixel_grads_kernel<<<grid_for(25LL * cin * cout, 256), 256, 0, stream>>>(dwm, cin, cout, dw);
+  AAE_LAUNCH_OK();
+  return AAE_OK;
+}
+
+int launch_space_to_depth(const float* in, float* out, int B, int h, int w, int C, cudaStream_t stream) {
+  AAE_REQUIRE(C % 4 == 0, "space_to_depth: C=%d must be a multiple of 4", C);
+  space_to_depth_kernel<<<grid_for((long long)B * h * w * C, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(in),
+                                                                                   reinterpret_cast<float4*>(out), B, h, w, C / 4);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }
