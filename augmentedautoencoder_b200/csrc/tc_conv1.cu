@@ -43,9 +43,10 @@ struct Conv1Params {
 template <int N>
 struct Conv1Smem {
   static constexpr int W_BYTES = 4 * N * 128;
-  static constexpr int PIX_BYTES = 2 * C1_PIX_ROWS * C1_PIX_LD * 4;   // double-buffered staged input rows, (hi|lo) words
+  static constexpr int PIX_BYTES = C1_PIX_ROWS * C1_PIX_LD * 4;       // staged input rows of one tile, (hi|lo) words
   static constexpr int OUT_BYTES = 2 * 32 * C1_OUT_LD;                // (hi, lo) output tile staged for bulk stores
-  static constexpr int TOTAL = W_BYTES + C1_STAGES * C1_STAGE + PIX_BYTES + OUT_BYTES + 1024 /*lut*/ + 1024 /*align*/ + 256;
+  static constexpr int RAW_BYTES = ((C1_PIX_ROWS * 128 * 3 * (int)sizeof(float) + 127) / 128) * 128;   // fp32 worst case
+  static constexpr int TOTAL = W_BYTES + C1_STAGES * C1_STAGE + PIX_BYTES + OUT_BYTES + RAW_BYTES + 1024 /*lut*/ + 1024 /*align*/ + 256;
 };
 
 template <bool U8>
@@ -67,10 +68,11 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* w_smem = smem;                                   // hi k0, hi k1, lo k0, lo k1 (N rows x 128 B each)
   uint8_t* a_smem = smem + S::W_BYTES;
-  uint32_t* pix = reinterpret_cast<uint32_t*>(a_smem + C1_STAGES * C1_STAGE);   // [2][C1_PIX_ROWS][C1_PIX_LD]
-  uint8_t* out_smem = reinterpret_cast<uint8_t*>(pix + 2 * C1_PIX_ROWS * C1_PIX_LD);   // [2 (hi,lo)][32][C1_OUT_LD]
+  uint32_t* pix = reinterpret_cast<uint32_t*>(a_smem + C1_STAGES * C1_STAGE);   // [C1_PIX_ROWS][C1_PIX_LD]
+  uint8_t* out_smem = reinterpret_cast<uint8_t*>(pix + C1_PIX_ROWS * C1_PIX_LD);   // [2 (hi,lo)][32][C1_OUT_LD]
   uint32_t* lut = reinterpret_cast<uint32_t*>(out_smem + S::OUT_BYTES);
-  uint64_t* w_full = reinterpret_cast<uint64_t*>(lut + 256);
+  uint8_t* raw_smem = reinterpret_cast<uint8_t*>(lut + 256);                    // raw input rows of the tile being staged
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(raw_smem + S::RAW_BYTES);
   uint64_t* a_full = w_full + 1;
   uint64_t* a_empty = a_full + C1_STAGES;
   uint64_t* acc_full = a_empty + C1_STAGES;
@@ -89,7 +91,7 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
     split_f16(v, h, l);
     lut[threadIdx.x] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
   }
-  for (int i = threadIdx.x; i < 2 * C1_PIX_ROWS * C1_PIX_LD; i += blockDim.x) pix[i] = 0u;   // left/right padding pixels stay zero
+  for (int i = threadIdx.x; i < C1_PIX_ROWS * C1_PIX_LD; i += blockDim.x) pix[i] = 0u;   // left/right padding pixels stay zero
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo);
     mbar_init(w_full, 1);
@@ -136,29 +138,28 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
         }
       }
     };
-    auto stage = [&](uint32_t* dst) {                        // registers -> staged (hi|lo) words
+    uint8_t* rawbuf = raw_smem;
+    auto stage = [&](uint32_t* dst) {                        // registers -> raw smem -> staged (hi|lo) words
+      // step 1: park the raw 16-byte pieces (conflict-free STS.128); step 2: every thread converts CONSECUTIVE elements, so
+      // the word stores to the staged rows are conflict-free too (converting 16 bytes per thread in place would put all 32
+      // lanes on two banks).
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const int u = r + v * 128;
+        if (u < C1_PIX_ROWS * ROWW / (U8 ? 16 : 4)) reinterpret_cast<uint4*>(rawbuf)[u] = raw[v];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int e = r; e < C1_PIX_ROWS * ROWW; e += 128) {
+        const int row = e / ROWW, col = e - row * ROWW;
+        uint32_t w;
         if (U8) {
-          const int row = u / (ROWW / 16), c16 = u - row * (ROWW / 16);
-          if (row >= C1_PIX_ROWS) continue;
-          uint32_t* o = dst + row * C1_PIX_LD + p.pad_l * CIN + c16 * 16;
-          const uint32_t w4[4] = {raw[v].x, raw[v].y, raw[v].z, raw[v].w};
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = lut[(w4[j >> 2] >> ((j & 3) * 8)) & 0xFFu];
+          w = lut[rawbuf[e]];
         } else {
-          const int row = u / (ROWW / 4), c4 = u - row * (ROWW / 4);
-          if (row >= C1_PIX_ROWS) continue;
-          uint32_t* o = dst + row * C1_PIX_LD + p.pad_l * CIN + c4 * 4;
-          const float f4[4] = {__uint_as_float(raw[v].x), __uint_as_float(raw[v].y), __uint_as_float(raw[v].z), __uint_as_float(raw[v].w)};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __half h, l;
-            split_f16(f4[j] * p.in_scale, h, l);
-            o[j] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
-          }
+          __half h, l;
+          split_f16(reinterpret_cast<const float*>(rawbuf)[e] * p.in_scale, h, l);
+          w = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
         }
+        dst[row * C1_PIX_LD + p.pad_l * CIN + col] = w;
       }
     };
     if (my_tiles > 0) {
@@ -171,7 +172,7 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
       const int s = i % C1_STAGES;
       const bool more = i + 1 < my_tiles;
       if (more) fetch((int)blockIdx.x + (i + 1) * (int)gridDim.x);
-      const uint32_t* src = pix + (i & 1) * C1_PIX_ROWS * C1_PIX_LD + 2 * dr * C1_PIX_LD + 2 * ow * CIN;
+      const uint32_t* src = pix + 2 * dr * C1_PIX_LD + 2 * ow * CIN;
       mbar_wait(&a_empty[s], ((uint32_t)(i / C1_STAGES) & 1u) ^ 1u);
       uint8_t* st = a_smem + s * C1_STAGE;
 #pragma unroll
@@ -195,8 +196,8 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_full[s]);
-      if (more) stage(pix + ((i + 1) & 1) * C1_PIX_ROWS * C1_PIX_LD);
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // staged rows of tile i+1 visible; tile i's rows free for reuse
+      if (more) stage(pix);                                   // (its internal barrier orders it after every thread's build of tile i)
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // staged rows of tile i+1 visible to all builders
     }
   } else if (warp < 8) {
     // ===================== epilogue =====================
