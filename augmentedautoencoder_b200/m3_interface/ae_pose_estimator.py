@@ -6,12 +6,14 @@ detections of a frame that share an object class are cropped, stacked and sent t
 in ONE batch per class, on the device that owns that class' (encoder, codebook) pair (multi-object routing, F14).
 """
 import configparser
+import ctypes as C
 import os
 
 import cv2
 import numpy as np
 import torch
 
+from .. import _lib
 from ..ae import factory, utils
 from ..ae.codebook import lift_pose
 from ..ae.session import Session
@@ -84,9 +86,23 @@ class AePoseEstimator(PoseEstInterface):
         scene_crop[(size - h) // 2:(size - h) // 2 + h, (size - w) // 2:(size - w) // 2 + w] = scene_img[y:y + h, x:x + w].copy()
         return cv2.resize(scene_crop, resize, interpolation=interpolation)
 
+    def extract_square_patches_device(self, frame_dev, boxes_xywh, pad_factor, patch_size):
+        """All crops of a frame in one launch (aae_extract_square_patches): the same pixels as ``extract_square_patch(...,
+        interpolation=cv2.INTER_LINEAR, black_borders=True)`` per box, bit for bit.  frame_dev: CUDA uint8 [H,W,3]."""
+        if patch_size[0] != patch_size[1]:
+            raise NotImplementedError("non-square patches")
+        n, ps = len(boxes_xywh), int(patch_size[0])
+        dev = frame_dev.device
+        boxes = torch.tensor(np.asarray(boxes_xywh, dtype=np.float32).reshape(n, 4)).to(dev)
+        out = torch.empty((n, ps, ps, 3), dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().aae_extract_square_patches(_lib.ptr(frame_dev), frame_dev.shape[0], frame_dev.shape[1], _lib.ptr(boxes), n,
+                                                         float(pad_factor), ps, _lib.ptr(out), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                   "extract_square_patches")
+        return out
+
     def process(self, bboxes, color_img, camK, depth_img=None, camPose=None, rois3ds=[], mm=False):
         H, W = color_img.shape[:2]
-        jobs = {}  # class -> list of (order, box_xywh, crop)
+        jobs = {}  # class -> list of (order, box_xywh)
         order = 0
         for box in bboxes:
             pred_clas = max(box.classes, key=box.classes.get)
@@ -95,20 +111,21 @@ class AePoseEstimator(PoseEstInterface):
             box_xywh = [box.xmin * W, box.ymin * H, (box.xmax - box.xmin) * W, (box.ymax - box.ymin) * H]
             if np.any(np.array(box_xywh) < 0):
                 continue
-            det_img = self.extract_square_patch(color_img, box_xywh, self.pad_factors[pred_clas], resize=self.patch_sizes[pred_clas],
-                                                interpolation=cv2.INTER_LINEAR, black_borders=True)
-            jobs.setdefault(pred_clas, []).append((order, box_xywh, det_img))
+            jobs.setdefault(pred_clas, []).append((order, box_xywh))
             order += 1
         results = [None] * order
         pending = []
+        frame_u8 = np.ascontiguousarray(color_img if color_img.dtype == np.uint8 else color_img.astype(np.uint8))
+        frames = {}   # device -> the frame, uploaded once per GPU
         for clas, items in jobs.items():  # launch every class' batch first (different GPUs run concurrently) ...
             cb, sess = self.all_codebooks[clas], self._sessions[clas]
-            crops = np.stack([it[2] for it in items])
-            if crops.dtype != np.uint8:
-                crops = crops.astype(np.float32)
-            with torch.cuda.device(sess.device):
-                xd = torch.from_numpy(crops).to(sess.device, non_blocking=True)
-                _, idx = cb.nearest_idx_device(xd, k=1, upright=self._upright)
+            dev = sess.device
+            with torch.cuda.device(dev):
+                if dev not in frames:
+                    frames[dev] = torch.from_numpy(frame_u8).to(dev, non_blocking=True)
+                crops = self.extract_square_patches_device(frames[dev], [it[1] for it in items], self.pad_factors[clas],
+                                                           self.patch_sizes[clas])
+                _, idx = cb.nearest_idx_device(crops, k=1, upright=self._upright)
             pending.append((clas, items, idx))
         for clas, items, idx in pending:     # ... then collect
             cb, sess = self.all_codebooks[clas], self._sessions[clas]
@@ -118,7 +135,7 @@ class AePoseEstimator(PoseEstInterface):
             radius = train_args.getfloat('Dataset', 'RADIUS')
             if cb.embed_obj_bbs_values is None:
                 cb.embed_obj_bbs_values = sess.run(cb.embed_obj_bbs_var)
-            for (o, box_xywh, _), i in zip(items, idcs):
+            for (o, box_xywh), i in zip(items, idcs):
                 Rs, ts = lift_pose(np.array([i]), cb._dataset.viewsphere_for_embedding, cb.embed_obj_bbs_values, box_xywh,
                                    np.asarray(camK), K_train, radius)
                 H_est = np.eye(4)

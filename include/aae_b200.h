@@ -160,6 +160,14 @@ AAE_API int aae_trainer_forward_backward(aae_trainer* h, const float* x_dev, con
 AAE_API int aae_trainer_get_grads(aae_trainer* h, int which, int layer, float* kernel_grad_any, float* bias_grad_any, void* stream);
 AAE_API int64_t aae_trainer_global_step(const aae_trainer* h);
 
+/* ---------------------------------------------------------------- Crop extraction ----------
+ * Batched AePoseEstimator.extract_square_patch(black_borders=True) + cv2.resize(INTER_LINEAR)
+ * (auto_pose/m3_interface/ae_pose_estimator.py:106-131,157-162): one launch for all detections of a frame, bit-exact
+ * with OpenCV's 8-bit fixed-point path.  image_dev: BGR uint8 [img_h, img_w, 3]; boxes_xywh_dev: [n,4] float32 pixel
+ * boxes (truncated to int like the reference); out_dev: NHWC uint8 [n, out_size, out_size, 3]. */
+AAE_API int aae_extract_square_patches(const uint8_t* image_dev, int img_h, int img_w, const float* boxes_xywh_dev,
+                                       int n_boxes, float pad_factor, int out_size, uint8_t* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

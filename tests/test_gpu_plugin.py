@@ -203,3 +203,29 @@ def test_async_streaming_call_matches_blocking_call(sess):
     for w, g_ in zip(want, got):
         assert g_.dtype == np.int64 and np.array_equal(w, g_)
     assert np.array_equal(cb.nearest_rotation_async(sess, batches[0].numpy()).result(), want[0])   # pageable numpy input works too
+
+
+def test_device_crops_are_bit_exact_with_opencv(sess, golden_dir):
+    """aae_extract_square_patches against (a) the crops the REFERENCE's extract_square_patch produced (golden) and (b) cv2 on
+    random boxes of many sizes, including up- and down-scaling and boxes touching the frame border."""
+    import cv2
+    from augmentedautoencoder_b200.m3_interface.ae_pose_estimator import AePoseEstimator
+    c = np.load(os.path.join(golden_dir, "crops_process.npz"))
+    scene = np.random.RandomState(int(c["scene_seed"])).randint(0, 256, size=tuple(c["scene_shape"]), dtype=np.uint8)
+    est = AePoseEstimator.__new__(AePoseEstimator)
+    frame = torch.from_numpy(scene).cuda()
+    got = est.extract_square_patches_device(frame, c["boxes"], 1.2, (128, 128)).cpu().numpy()
+    assert np.array_equal(got, c["crops_black_borders_linear"])
+    rng = np.random.RandomState(3)
+    boxes = []
+    for _ in range(200):
+        w, h = rng.randint(8, 400), rng.randint(8, 400)
+        x, y = rng.randint(0, 640 - min(w, 639)), rng.randint(0, 480 - min(h, 479))
+        w, h = min(w, 640 - x), min(h, 480 - y)
+        boxes.append([x + rng.rand() * 0.9, y + rng.rand() * 0.9, w + rng.rand() * 0.9, h + rng.rand() * 0.9])
+    boxes += [[0, 0, 640, 480], [0, 0, 1, 1], [639, 479, 1, 1], [100, 100, 128, 128], [10, 20, 256, 256]]
+    for pf in (1.2, 1.0, 1.37):
+        got = est.extract_square_patches_device(frame, boxes, pf, (128, 128)).cpu().numpy()
+        for b, g_ in zip(boxes, got):
+            want = est.extract_square_patch(scene, b, pf, resize=(128, 128), interpolation=cv2.INTER_LINEAR, black_borders=True)
+            assert np.array_equal(g_, want), (b, pf, int((g_ != want).sum()))
