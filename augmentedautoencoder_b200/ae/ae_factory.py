@@ -224,9 +224,24 @@ class Saver(object):
         np.savez(path, **self.variables())
         return path
 
+    def save_tf(self, session, save_path, global_step=None):
+        """Same variables as a TensorFlow tensor bundle (``<save_path>-<step>.index`` / ``.data-00000-of-00001``) plus the
+        ``checkpoint`` state file, i.e. what the reference's ``saver.save`` leaves behind (ae_train.py:134-135)."""
+        from .tf_checkpoint import write_tf_checkpoint
+        prefix = "%s-%d" % (save_path, int(global_step)) if global_step is not None else save_path
+        write_tf_checkpoint(prefix, self.variables())
+        with open(os.path.join(os.path.dirname(prefix), "checkpoint"), "w") as f:
+            f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (os.path.basename(prefix), os.path.basename(prefix)))
+        return prefix
+
     def restore(self, session, path):
-        data = np.load(path)
-        weights = {k: data[k] for k in data.files}
+        """path: ``chkpt-<step>.npz`` or the prefix of a TensorFlow checkpoint (``.../chkpt-30000``)."""
+        if path.endswith(".npz"):
+            data = np.load(path)
+            weights = {k: data[k] for k in data.files}
+        else:
+            from .tf_checkpoint import read_tf_checkpoint
+            weights = read_tf_checkpoint(path)
         for m in self._modules:
             if isinstance(m, Codebook):
                 if m.embedding_normalized.name in weights:
@@ -241,7 +256,19 @@ class Saver(object):
 
 
 def restore_checkpoint(session, saver, ckpt_dir, at_step=None):
-    """Latest ``chkpt-<step>.npz`` in ckpt_dir, or the one whose name contains ``at_step`` (ae_factory.py:149-172)."""
+    """Latest checkpoint in ckpt_dir, or the one whose name contains ``at_step`` (ae_factory.py:149-172).  A TensorFlow
+    ``checkpoint`` state file takes precedence (the reference's own layout); otherwise ``chkpt-<step>.npz`` files."""
+    from .tf_checkpoint import latest_checkpoint
+    latest, every = latest_checkpoint(ckpt_dir)
+    if latest is not None:
+        if at_step is None:
+            saver.restore(session, latest)
+            return latest
+        for p in every:
+            if str(at_step) in str(p):
+                saver.restore(session, p)
+                return p
+        raise FileNotFoundError('No checkpoint for step %s in %s' % (at_step, ckpt_dir))
     paths = sorted(glob.glob(os.path.join(ckpt_dir, "chkpt-*.npz")), key=lambda p: int(p.rsplit("-", 1)[1][:-4]))
     if not paths:
         raise FileNotFoundError('No checkpoint found. Expected one in: %s' % ckpt_dir)

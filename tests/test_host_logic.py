@@ -113,3 +113,58 @@ def test_saver_round_trip(tmp_path):
     assert np.array_equal(cb2.embedding_normalized.value(), E)
     with pytest.raises(FileNotFoundError):
         factory.restore_checkpoint(None, factory.Saver([enc2]), str(tmp_path / "nothing"))
+
+
+def test_tf_tensor_bundle_round_trip(tmp_path):
+    from augmentedautoencoder_b200.ae.tf_checkpoint import crc32c, latest_checkpoint, read_tf_checkpoint, write_tf_checkpoint
+    assert crc32c(b"123456789") == 0xE3069283                      # the standard CRC-32C check value
+    rng = np.random.RandomState(0)
+    tensors = {"obj/conv2d/kernel": rng.randn(5, 5, 3, 8).astype(np.float32), "obj/conv2d/bias": rng.randn(8).astype(np.float32),
+               "obj/conv2d_1/kernel": rng.randn(5, 5, 8, 4).astype(np.float32), "obj/embed_obj_bbs_var": rng.randint(0, 700, (36, 4)).astype(np.int32),
+               "obj/global_step": np.asarray(30000, dtype=np.int64), "obj/embedding_normalized": rng.randn(36, 16).astype(np.float32)}
+    for i in range(40):                                            # > one restart interval of prefix-compressed keys
+        tensors["obj/extra_%02d/v" % i] = rng.randn(3, i + 1).astype(np.float32)
+    prefix = str(tmp_path / "checkpoints" / "chkpt-30000")
+    write_tf_checkpoint(prefix, tensors)
+    assert os.path.exists(prefix + ".index") and os.path.exists(prefix + ".data-00000-of-00001")
+    got = read_tf_checkpoint(prefix, verify_crc=True)
+    assert set(got) == set(tensors)
+    for k, v in tensors.items():
+        assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v), k
+    assert set(read_tf_checkpoint(prefix, names={"obj/conv2d/bias"})) == {"obj/conv2d/bias"}
+    with open(prefix + ".index", "r+b") as f:                      # corrupt the magic -> loud failure
+        f.seek(-1, 2)
+        f.write(b"\x00")
+    with pytest.raises(ValueError):
+        read_tf_checkpoint(prefix)
+    assert latest_checkpoint(str(tmp_path)) == (None, [])
+
+
+def test_restore_checkpoint_reads_tensorflow_layout(tmp_path):
+    from augmentedautoencoder_b200 import _lib
+    from augmentedautoencoder_b200.ae import factory
+    from augmentedautoencoder_b200.ae import session as S
+    from augmentedautoencoder_b200.ae.codebook import Codebook
+    from augmentedautoencoder_b200.ae.encoder import Encoder
+    _lib.lib()
+    ds = Dataset(None, min_n_views=12, num_cyclo=4, radius=700)
+
+    def make(seed):
+        with S.variable_scope("e1"):
+            enc = Encoder(S.placeholder(np.float32, [None, 32, 32, 3]), 16, [8, 16], 5, [2, 2], False, seed=seed)
+            return enc, Codebook(enc, ds, True)
+    enc, cb = make(1)
+    cb.embedding_normalized.assign(np.random.RandomState(0).randn(ds.embedding_size, 16).astype(np.float32))
+    ckdir = tmp_path / "checkpoints"
+    factory.Saver([enc, cb]).save_tf(None, str(ckdir / "chkpt"), global_step=20000)
+    prefix = factory.Saver([enc, cb]).save_tf(None, str(ckdir / "chkpt"), global_step=30000)
+    (ckdir / "checkpoint").write_text('model_checkpoint_path: "chkpt-30000"\nall_model_checkpoint_paths: "chkpt-20000"\n'
+                                      'all_model_checkpoint_paths: "chkpt-30000"\n')
+    enc2, cb2 = make(2)
+    assert factory.restore_checkpoint(None, factory.Saver([enc2, cb2]), str(ckdir)) == prefix
+    for k, v in enc.get_weights().items():
+        assert np.array_equal(enc2.get_weights()[k], v)
+    assert np.array_equal(cb2.embedding_normalized.value(), cb.embedding_normalized.value())
+    assert factory.restore_checkpoint(None, factory.Saver([enc2, cb2]), str(ckdir), at_step=20000).endswith("chkpt-20000")
+    with pytest.raises(FileNotFoundError):
+        factory.restore_checkpoint(None, factory.Saver([enc2, cb2]), str(ckdir), at_step=12345)
