@@ -81,3 +81,54 @@ def test_tc_end_to_end_256_crops_index_parity(sess):
             assert abs(c64[j, got[b]] - c64[j, want[b]]) < 2e-6, ("index mismatch beyond fp32 resolution", b)
     assert len(bad) <= 1
     assert np.max(np.abs(s_dev.cpu().numpy()[:, 0] - cos[np.arange(256), got])) <= COS_TOL
+
+
+@pytest.mark.parametrize("batch", [1, 2, 63, 127, 129, 255, 300])
+def test_tc_path_agrees_with_fp32_path_for_ragged_batches(sess, batch):
+    """Tile-boundary cases: batches that do not fill a 128-pixel tile / a CTA pair / a 128-query block, and a batch larger
+    than max_batch (chunked by the host wrapper).  The tensor-core path must give the fp32 path's indices and scores."""
+    p = O.make_encoder_params(42, bias_scale=0.03)
+    E = O.make_codebook(9, n=36 * 700 + 5, num_cyclo=1, duplicate_cyclo_endpoints=False)
+    crops = O.make_crops_u8(77 + batch, batch)
+    res = []
+    for prec in (0, 1):
+        enc = _enc(prec, 256, p)
+        cb = _codebook(enc, E, num_cyclo=1, max_batch=256, precision=prec)
+        z = sess.run(enc.z, {enc.x: crops})
+        s, i = cb.nearest_idx_device(torch.from_numpy(crops).cuda())
+        res.append((z, s.cpu().numpy()[:, 0], i.cpu().numpy()[:, 0]))
+    (z0, s0, i0), (z1, s1, i1) = res
+    assert z1.shape == (batch, 128)
+    assert np.max(np.abs(z0 - z1)) < 2e-5 * np.abs(z0).max()
+    assert np.max(np.abs(s0 - s1)) < COS_TOL
+    bad = np.nonzero(i0 != i1)[0]
+    cos = O.cos_similarity(z0[bad].astype(np.float64), E.astype(np.float64)) if len(bad) else None
+    for j, b in enumerate(bad):
+        assert abs(cos[j, i0[b]] - cos[j, i1[b]]) < 2e-6, (b, i0[b], i1[b])
+
+
+def test_c_abi_rejects_bad_calls_without_crashing(sess):
+    import ctypes as C
+    from augmentedautoencoder_b200 import _lib
+    lib = _lib.lib()
+    p = O.make_encoder_params(42)
+    enc = _enc(1, 8, p)
+    h = enc.handle(sess.device)
+    x = torch.zeros((16, 128, 128, 3), dtype=torch.uint8, device="cuda")
+    z = torch.zeros((16, 128), device="cuda")
+    assert lib.aae_encoder_forward_u8(h, _lib.ptr(x), 16, _lib.ptr(z), None) == -1          # batch > max_batch
+    assert b"max_batch" in lib.aae_last_error_string()
+    assert lib.aae_encoder_forward_u8(h, None, 4, _lib.ptr(z), None) == -1
+    assert lib.aae_encoder_forward_u8(h, _lib.ptr(x), 0, _lib.ptr(z), None) == -1
+    cbh = C.c_void_p()
+    E = O.make_codebook(1, n=100, num_cyclo=1, duplicate_cyclo_endpoints=False)
+    assert lib.aae_codebook_create(0, _lib.ptr(E), 100, 96, 1, 0, 8, 1, C.byref(cbh)) != 0     # TC match is built for latent 128
+    assert b"latent" in lib.aae_last_error_string() and not cbh.value
+    assert lib.aae_codebook_create(0, _lib.ptr(E), 100, 128, 1, 0, 8, 1, C.byref(cbh)) == 0
+    s = torch.zeros((4, 1), device="cuda")
+    i = torch.zeros((4, 1), dtype=torch.int32, device="cuda")
+    assert lib.aae_codebook_match(cbh, _lib.ptr(z), 4, 101, 0, _lib.ptr(s), _lib.ptr(i), None) == -1   # k > rows
+    assert lib.aae_codebook_match(cbh, _lib.ptr(z), 9, 1, 0, _lib.ptr(s), _lib.ptr(i), None) == -1     # batch > max_batch
+    assert lib.aae_codebook_destroy(cbh) == 0
+    assert lib.aae_encoder_forward_u8(h, _lib.ptr(x), 4, _lib.ptr(z), None) == 0                          # handle still healthy
+    torch.cuda.synchronize()
