@@ -14,7 +14,7 @@ from .utils import lazy_property
 class Decoder(_DeviceModule):
 
     def __init__(self, reconstruction_target, latent_code, num_filters, kernel_size, strides, loss, bootstrap_ratio,
-                 auxiliary_mask, batch_norm, is_training=False, max_batch=64, seed=43, n_encoder_convs=None):
+                 auxiliary_mask, batch_norm, is_training=False, max_batch=64, seed=43, n_encoder_convs=None, precision=None):
         if batch_norm:
             raise NotImplementedError("BATCH_NORMALIZATION: True is not supported")
         if auxiliary_mask:
@@ -51,7 +51,7 @@ class Decoder(_DeviceModule):
             cin = f
         # the C ABI takes the encoder-order filters/strides and reverses them itself (aae_net_cfg)
         self._init_module((h, w, c, list(reversed(self._num_filters)), list(reversed(self._strides)), self._kernel_size,
-                           latent, self.max_batch, _lib.PREC_FP32_SIMT), var_shapes, seed)
+                           latent, self.max_batch, _lib.PREC_FP32_SIMT if precision is None else int(precision)), var_shapes, seed)
         self.reconstr_loss
 
     @property

@@ -169,6 +169,7 @@ struct aae_decoder {
   DevBuf dense_out;         // [max_batch, h0, w0, f0]  (post ReLU)
   std::vector<ConvLayer> conv;  // forward order; conv.back() is the sigmoid output layer
   DevBuf partials;
+  TcDecoder* tc = nullptr;      // tensor-core execution plan (AAE_PREC_TC_SPLIT, forward only)
   int last_batch = 0;
 };
 
@@ -551,6 +552,7 @@ extern "C" int aae_decoder_create(int device, const aae_net_cfg* cfg, aae_decode
     ih = R.out_h; ic = R.out_c;
   }
   if (status == AAE_OK) status = h->partials.alloc((size_t)4 << 20);
+  if (status == AAE_OK && cfg->precision == AAE_PREC_TC_SPLIT) status = tc_decoder_create(device, cfg, &h->tc);
   if (status != AAE_OK) { aae_decoder_destroy(h); return status; }
   *out = h;
   return AAE_OK;
@@ -561,6 +563,7 @@ extern "C" int aae_decoder_destroy(aae_decoder* h) {
   DeviceGuard g(h->device);
   h->dense_w.release(); h->dense_b.release(); h->dense_out.release(); h->partials.release();
   for (auto& L : h->conv) { L.w.release(); L.b.release(); L.out.release(); L.wm.release(); L.bias4.release(); }
+  if (h->tc) tc_decoder_destroy(h->tc);
   delete h;
   return AAE_OK;
 }
@@ -575,6 +578,7 @@ extern "C" int aae_decoder_set_weights(aae_decoder* h, int layer, const float* k
   if (kernel_any) AAE_TRY(copy_any(w.p, kernel_any, w.n * sizeof(float), s));
   if (bias_any) AAE_TRY(copy_any(b.p, bias_any, b.n * sizeof(float), s));
   if (layer > 0) h->conv[layer - 1].wm_dirty = true;
+  if (h->tc) AAE_TRY(tc_decoder_pack_weights(h->tc, layer, kernel_any ? w.p : nullptr, bias_any ? b.p : nullptr, s));
   AAE_CUDA_OK(cudaStreamSynchronize(s));
   return AAE_OK;
 }
@@ -634,6 +638,7 @@ extern "C" int aae_decoder_forward(aae_decoder* h, const float* z_dev, int batch
   AAE_REQUIRE(batch >= 1 && batch <= h->cfg.max_batch, "batch %d outside [1, max_batch=%d]", batch, h->cfg.max_batch);
   DeviceGuard g(h->device);
   h->last_batch = batch;
+  if (h->tc) return tc_decoder_forward(h->tc, z_dev, batch, x_out_dev, (cudaStream_t)stream);
   return decoder_forward_impl(h, z_dev, batch, x_out_dev, (cudaStream_t)stream);
 }
 
@@ -668,7 +673,7 @@ extern "C" int aae_trainer_create(aae_encoder* enc, aae_decoder* dec, int bootst
   *out = nullptr;
   AAE_REQUIRE(enc && dec, "null handle");
   AAE_REQUIRE(enc->device == dec->device, "encoder and decoder live on different devices");
-  AAE_REQUIRE(enc->tc == nullptr, "training runs on the AAE_PREC_FP32_SIMT encoder path");
+  AAE_REQUIRE(enc->tc == nullptr && dec->tc == nullptr, "training runs on the AAE_PREC_FP32_SIMT encoder / decoder path");
   AAE_REQUIRE(enc->cfg.max_batch == dec->cfg.max_batch && enc->cfg.in_h == dec->cfg.in_h, "encoder/decoder geometry mismatch");
   DeviceGuard g(enc->device);
   aae_trainer* h = new (std::nothrow) aae_trainer();

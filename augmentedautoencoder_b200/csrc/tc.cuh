@@ -27,6 +27,12 @@ int tc_encoder_activation(TcEncoder* h, int layer, int B, const float** ptr, int
 void tc_encoder_enable_timer(TcEncoder* h, bool on);
 int tc_encoder_read_timer(TcEncoder* h, float* ms, int cap);
 
+struct TcDecoder;
+int tc_decoder_create(int device, const aae_net_cfg* cfg, TcDecoder** out);
+void tc_decoder_destroy(TcDecoder* h);
+int tc_decoder_pack_weights(TcDecoder* h, int layer, const float* w_dev, const float* b_dev, cudaStream_t s);
+int tc_decoder_forward(TcDecoder* h, const float* z_dev, int B, float* x_out, cudaStream_t s);
+
 int tc_codebook_create(int device, const float* E_dev, int64_t n_rows, int latent, int max_batch, TcCodebook** out);
 void tc_codebook_destroy(TcCodebook* h);
 int tc_codebook_match(TcCodebook* h, const float* E_dev, const float* z_dev, int B, int64_t row_offset, int num_cyclo, int upright,

@@ -58,7 +58,13 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 }
 
 // ------------------------------------------------------------------------------------------------- kernel
-enum TcOutMode : int { OUT_S2D_SPLIT = 0, OUT_PLAIN_SPLIT = 1, OUT_F32 = 2 };
+enum TcOutMode : int {
+  OUT_S2D_SPLIT = 0,      // (hi, lo) fp16, space-to-depth layout of the next stride-2 conv
+  OUT_PLAIN_SPLIT = 1,    // (hi, lo) fp16, plain [M, N]
+  OUT_F32 = 2,            // fp32 [splits, M, N] raw accumulators (split-K partials)
+  OUT_D2S_SPLIT = 3,      // (hi, lo) fp16, depth-to-space: column (cls, co) of pixel (b,i,j) -> pixel (2i+py, 2j+px) of [B,2OH,2OW,N/4]
+  OUT_D2S_F32 = 4         // fp32, depth-to-space with `cout_real` channels per parity (decoder output layer, N padded)
+};
 
 struct TcGemmParams {
   int M;                 // valid output rows (pixels, or batch rows for the dense layer)
@@ -73,12 +79,82 @@ struct TcGemmParams {
   float unscale;         // 1 / (scale_A * scale_W)
   float out_scale;       // scale applied before the hi/lo split of the output (next layer's scale_A)
   const float* bias;
-  int relu;
+  int relu;              // activation: 0 none, 1 ReLU, 2 sigmoid
+  int cout_real;         // OUT_D2S_F32: real channels per parity class (columns >= 4*cout_real are padding)
   int out_mode;
   __half* out_hi;
   __half* out_lo;
   float* out_f32;        // OUT_F32: [splits, M, N]
 };
+
+
+// ------------------------------------------------------------------------------------------------- shared epilogue
+struct TcRow {
+  bool valid;
+  int b, i, j;            // pixel coordinates on the OH x OW grid
+  long long row_off;      // element offset of column 0 for the row-contiguous output modes
+};
+
+__device__ __forceinline__ TcRow tc_decode_row(const TcGemmParams& p, int m) {
+  TcRow r;
+  r.valid = m < p.M;
+  r.b = r.i = r.j = 0;
+  r.row_off = 0;
+  if (!r.valid) return r;
+  const int hw = p.OH * p.OW;
+  r.b = m / hw;
+  const int rem = m - r.b * hw;
+  r.i = rem / p.OW;
+  r.j = rem - r.i * p.OW;
+  if (p.out_mode == OUT_S2D_SPLIT)
+    r.row_off = ((long long)(r.b * (p.OH >> 1) + (r.i >> 1)) * (p.OW >> 1) + (r.j >> 1)) * (4LL * p.N) + (((r.i & 1) << 1) | (r.j & 1)) * p.N;
+  else
+    r.row_off = (long long)m * p.N;
+  return r;
+}
+
+// f[0..31]: accumulator values (already hh + cross, times unscale) of columns n .. n+31 of this thread's row
+__device__ __forceinline__ void tc_store_chunk(const TcGemmParams& p, const TcRow& r, int n, float (&f)[32], int split_z) {
+  if (p.out_mode == OUT_F32) {
+    float* dst = p.out_f32 + (long long)split_z * p.M * p.N + r.row_off + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float a = f[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+    if (p.relu == 1) a = fmaxf(a, 0.f);
+    else if (p.relu == 2) a = 1.f / (1.f + expf(-a));
+    f[j] = a;
+  }
+  if (p.out_mode == OUT_D2S_F32) {
+    const int cr = p.cout_real;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int nn = n + j;
+      if (nn >= 4 * cr) continue;
+      const int cls = nn / cr, co = nn - cls * cr;
+      p.out_f32[((long long)(r.b * 2 * p.OH + 2 * r.i + (cls >> 1)) * (2 * p.OW) + 2 * r.j + (cls & 1)) * cr + co] = f[j];
+    }
+    return;
+  }
+  long long off = r.row_off + n;
+  if (p.out_mode == OUT_D2S_SPLIT) {
+    const int cq = p.N >> 2, cls = n / cq, co = n - cls * cq;     // a 32-column chunk never straddles a parity class (cq % 32 == 0)
+    off = ((long long)(r.b * 2 * p.OH + 2 * r.i + (cls >> 1)) * (2 * p.OW) + 2 * r.j + (cls & 1)) * cq + co;
+  }
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) split_f16x2(f[j] * p.out_scale, f[j + 1] * p.out_scale, hi[j >> 1], lo[j >> 1]);
+  uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
+  uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+    dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+  }
+}
 
 template <int N_TILE, int STAGES, int KCH = 64>
 struct TcSmem {
@@ -174,22 +250,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int m = m0 + r;
+    const TcRow row = tc_decode_row(p, m0 + q * 32 + lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const bool valid = m < p.M;
-    long long row_off = 0;
-    if (valid) {
-      if (p.out_mode == OUT_S2D_SPLIT) {
-        const int hw = p.OH * p.OW;
-        const int b = m / hw, rem = m - b * hw;
-        const int oh = rem / p.OW, ow = rem - oh * p.OW;
-        row_off = ((long long)(b * (p.OH >> 1) + (oh >> 1)) * (p.OW >> 1) + (ow >> 1)) * (4LL * p.N) + (((oh & 1) << 1) | (ow & 1)) * p.N;
-      } else {
-        row_off = (long long)m * p.N;
-      }
-    }
     const bool has_work = it_end > it_begin;
 #pragma unroll 1
     for (int c = 0; c < N_TILE / 32; ++c) {
@@ -197,38 +260,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
       tmem_ld_wait();
-      if (!valid) continue;
       const int n = n0 + c * 32;
-      if (n >= p.N) continue;
+      if (!row.valid || n >= p.N) continue;
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = has_work ? (__uint_as_float(v[j]) + __uint_as_float(x[j])) * p.unscale : 0.f;
-      if (p.out_mode == OUT_F32) {
-        float* dst = p.out_f32 + (long long)blockIdx.z * p.M * p.N + row_off + n;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-      } else {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float a = f[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-          float b = f[j + 1] + (p.bias ? __ldg(p.bias + n + j + 1) : 0.f);
-          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-          a *= p.out_scale; b *= p.out_scale;
-          __half ah, al, bh, bl;
-          split_f16(a, ah, al);
-          split_f16(b, bh, bl);
-          hi[j >> 1] = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
-          lo[j >> 1] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
-        }
-        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + row_off + n);
-        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + row_off + n);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-        }
-      }
+      tc_store_chunk(p, row, n, f, (int)blockIdx.z);
     }
   }
   tc_fence_before();
@@ -332,46 +369,21 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int m = m0 + r;
+    const TcRow row = tc_decode_row(p, m0 + q * 32 + lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const bool valid = m < p.M;
-    long long row_off = 0;
-    if (valid) {
-      if (p.out_mode == OUT_S2D_SPLIT) {
-        const int hw = p.OH * p.OW;
-        const int b = m / hw, rem = m - b * hw;
-        const int oh = rem / p.OW, ow = rem - oh * p.OW;
-        row_off = ((long long)(b * (p.OH >> 1) + (oh >> 1)) * (p.OW >> 1) + (ow >> 1)) * (4LL * p.N) + (((oh & 1) << 1) | (ow & 1)) * p.N;
-      } else {
-        row_off = (long long)m * p.N;
-      }
-    }
 #pragma unroll 1
     for (int c = 0; c < N_TILE / 32; ++c) {
       uint32_t v[32], x[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
       tmem_ld_wait();
-      if (!valid) continue;
       const int n = n0 + c * 32;
-      if (n >= p.N) continue;
-      uint32_t hi[16], lo[16];
+      if (!row.valid || n >= p.N) continue;
+      float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float a = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * p.unscale + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-        float b = (__uint_as_float(v[j + 1]) + __uint_as_float(x[j + 1])) * p.unscale + (p.bias ? __ldg(p.bias + n + j + 1) : 0.f);
-        if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-        split_f16x2(a * p.out_scale, b * p.out_scale, hi[j >> 1], lo[j >> 1]);
-      }
-      uint4* dh = reinterpret_cast<uint4*>(p.out_hi + row_off + n);
-      uint4* dl = reinterpret_cast<uint4*>(p.out_lo + row_off + n);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-        dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-      }
+      for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * p.unscale;
+      tc_store_chunk(p, row, n, f, 0);
     }
   }
   tc_fence_before();
@@ -713,6 +725,194 @@ int tc_encoder_activation(TcEncoder* h, int layer, int B, const float** ptr, int
   AAE_CUDA_OK(cudaStreamSynchronize(s));
   *ptr = h->dbg;
   *count = (int64_t)n;
+  return AAE_OK;
+}
+
+
+// ================================================================================================= decoder plan
+// Decoder.x (auto_pose/ae/decoder.py:36-84) on the tensor cores, in the sub-pixel form: dense 128 -> 8*8*512 (+ReLU), then
+// every "nearest x2 upsample + conv5x5 (+ReLU)" as ONE GEMM  [B*h*w pixels] x [9*Cin] x [4*Cout]  over the LOW-resolution
+// activation (plain NHWC (hi, lo) fp16, 3x3 taps as unit-stride TMA boxes) with the taps of the 5x5 kernel pre-summed per
+// output parity; the epilogue scatters column (parity, co) of pixel (i, j) to pixel (2i+py, 2j+px) of the next layer's input
+// (depth-to-space).  The output layer (Cout = 3 -> N = 12, padded to 32) applies the sigmoid and writes fp32 NHWC.
+namespace {
+
+__global__ void split_scale_kernel(const float* __restrict__ x, long long n, float scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    __half h, l;
+    split_f16(x[i] * scale, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+__global__ void tile_bias_kernel(const float* __restrict__ b, int cout, int n_pad, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) out[i] = i < 4 * cout ? b[i % cout] : 0.f;
+}
+
+}  // namespace
+
+struct TcDecoder {
+  int device;
+  aae_net_cfg cfg;
+  std::vector<TcLayer> layers;     // [0] dense_1, [1..L-1] sub-pixel convs, [L] sub-pixel output layer
+  std::vector<float*> bias_dev;    // per layer: bias in GEMM-column order (dense: the caller's; convs: tiled 4x, padded)
+  float* wm_tmp = nullptr;         // fp32 merged-weight scratch
+  size_t wm_floats = 0;
+};
+
+static int tc_layer_alloc_common(TcLayer& T, int B, bool pair_ok) {
+  int st;
+  const int B_pad = (int)ceil_div(B, T.BB) * T.BB;
+  const size_t act = (size_t)B_pad * T.in_h * T.in_w * T.in_c;
+  if ((st = dev_alloc((void**)&T.in_hi, act * sizeof(__half))) != AAE_OK) return st;
+  if ((st = dev_alloc((void**)&T.in_lo, act * sizeof(__half))) != AAE_OK) return st;
+  const uint64_t K = (uint64_t)T.taps * T.in_c;
+  const int rows = (int)ceil_div(T.gp.N, T.n_tile) * T.n_tile;
+  if ((st = dev_alloc((void**)&T.w_hi, (size_t)rows * K * sizeof(__half))) != AAE_OK) return st;
+  if ((st = dev_alloc((void**)&T.w_lo, (size_t)rows * K * sizeof(__half))) != AAE_OK) return st;
+  {
+    const uint64_t dims[4] = {(uint64_t)T.in_c, (uint64_t)T.in_w, (uint64_t)T.in_h, (uint64_t)B_pad};
+    const uint64_t strides[3] = {(uint64_t)T.in_c * 2, (uint64_t)T.in_w * T.in_c * 2, (uint64_t)T.in_h * T.in_w * T.in_c * 2};
+    const uint32_t box[4] = {(uint32_t)T.kch, (uint32_t)T.BW, (uint32_t)T.BH, (uint32_t)T.BB};
+    if ((st = make_tmap_f16(&T.tm_a_hi, T.in_hi, 4, dims, strides, box, 2 * T.kch)) != AAE_OK) return st;
+    if ((st = make_tmap_f16(&T.tm_a_lo, T.in_lo, 4, dims, strides, box, 2 * T.kch)) != AAE_OK) return st;
+  }
+  {
+    const uint64_t dims[2] = {K, (uint64_t)rows};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {(uint32_t)T.kch, (uint32_t)T.n_tile};
+    if ((st = make_tmap_f16(&T.tm_w_hi, T.w_hi, 2, dims, strides, box, 2 * T.kch)) != AAE_OK) return st;
+    if ((st = make_tmap_f16(&T.tm_w_lo, T.w_lo, 2, dims, strides, box, 2 * T.kch)) != AAE_OK) return st;
+    T.pair = pair_ok && T.n_tile == 256 && T.gp.N % 256 == 0 && getenv("AAE_TC_1CTA") == nullptr;
+    if (T.pair) {
+      const uint32_t box2[2] = {(uint32_t)T.kch, 128};
+      if ((st = make_tmap_f16(&T.tm_w2_hi, T.w_hi, 2, dims, strides, box2, 2 * T.kch)) != AAE_OK) return st;
+      if ((st = make_tmap_f16(&T.tm_w2_lo, T.w_lo, 2, dims, strides, box2, 2 * T.kch)) != AAE_OK) return st;
+    }
+  }
+  return AAE_OK;
+}
+
+int tc_decoder_create(int device, const aae_net_cfg* cfg, TcDecoder** out) {
+  *out = nullptr;
+  AAE_REQUIRE(aae_device_supported(device), "AAE_PREC_TC_SPLIT needs a compute-capability 10.x device (tcgen05/TMEM)");
+  const int L = cfg->num_layers;
+  AAE_REQUIRE(cfg->kernel_size == 5 && cfg->in_h == cfg->in_w, "AAE_PREC_TC_SPLIT decoder: kernel 5, square crops");
+  TcDecoder* h = new TcDecoder();
+  h->device = device;
+  h->cfg = *cfg;
+  const int B = cfg->max_batch;
+  int h0 = cfg->in_h;
+  for (int i = 0; i < L; ++i) h0 /= 2;
+  std::vector<int> nf(L);
+  for (int i = 0; i < L; ++i) nf[i] = cfg->filters[L - 1 - i];
+  int st = AAE_OK;
+  for (int l = 0; l <= L && st == AAE_OK; ++l) {
+    TcLayer T;
+    memset(&T.gp, 0, sizeof(T.gp));
+    TcGemmParams& g = T.gp;
+    T.kch = 32;
+    if (l == 0) {                                   // dense_1: [B, latent] x [latent, h0*h0*f0]
+      T.in_h = T.in_w = 1; T.in_c = cfg->latent; T.out_h = T.out_w = 1; T.out_c = h0 * h0 * nf[0];
+      T.taps = 1; T.BW = 1; T.BH = 1; T.BB = 128; T.n_tile = 256;
+      g.N = T.out_c; g.OH = g.OW = 1; g.relu = 1; g.out_mode = OUT_PLAIN_SPLIT;
+      if (cfg->latent % 32 != 0 || T.out_c % 256 != 0) { set_error("tc decoder: latent %% 32 and dense width %% 256 required"); st = AAE_ERR_UNSUPPORTED; break; }
+    } else {                                        // sub-pixel conv on the (h x w x C) low-resolution activation
+      const int hh = h0 << (l - 1);
+      T.in_h = T.in_w = hh; T.in_c = nf[l - 1];
+      const int cout = l < L ? nf[l] : cfg->in_c;
+      T.out_h = T.out_w = 2 * hh; T.out_c = cout;
+      T.taps = 9;
+      if (hh > 128 || (hh & (hh - 1)) || T.in_c % 32 != 0 || (l < L && cout % 64 != 0)) {
+        set_error("tc decoder: layer %d unsupported (power-of-two size <= 128, Cin %% 32, Cout %% 64)", l); st = AAE_ERR_UNSUPPORTED; break;
+      }
+      T.BW = hh; T.BH = std::min(hh, 128 / T.BW); T.BB = 128 / (T.BW * T.BH);
+      g.OH = g.OW = hh;
+      if (l < L) { g.N = 4 * cout; T.n_tile = 256; g.relu = 1; g.out_mode = OUT_D2S_SPLIT; }
+      else { g.N = 32; T.n_tile = 32; g.relu = 2; g.out_mode = OUT_D2S_F32; g.cout_real = cout;
+             if (4 * cout > 32) { set_error("tc decoder: output channels > 8 unsupported"); st = AAE_ERR_UNSUPPORTED; break; } }
+    }
+    g.BW = T.BW; g.BH = T.BH; g.taps = T.taps; g.chunks_per_tap = T.in_c / T.kch;
+    g.iters_per_split = g.taps * g.chunks_per_tap;
+    for (int t = 0; t < T.taps; ++t) {
+      g.tap_di[t] = (int8_t)(T.taps == 1 ? 0 : t / 3 - 1);
+      g.tap_dj[t] = (int8_t)(T.taps == 1 ? 0 : t % 3 - 1);
+      g.tap_ch[t] = 0;
+    }
+    g.unscale = 1.f / (ACT_SCALE * W_SCALE);
+    g.out_scale = ACT_SCALE;
+    if ((st = tc_layer_alloc_common(T, B, /*pair_ok=*/l > 0)) != AAE_OK) { h->layers.push_back(T); break; }
+    h->layers.push_back(T);
+    float* bz = nullptr;
+    if (l > 0) st = dev_alloc((void**)&bz, (size_t)std::max(g.N, 32) * sizeof(float));
+    h->bias_dev.push_back(bz);
+    h->wm_floats = std::max(h->wm_floats, (size_t)9 * T.in_c * 4 * T.out_c);
+  }
+  if (st == AAE_OK) st = dev_alloc((void**)&h->wm_tmp, h->wm_floats * sizeof(float));
+  if (st == AAE_OK) {
+    for (size_t i = 0; i + 1 < h->layers.size(); ++i) {
+      h->layers[i].gp.out_hi = h->layers[i + 1].in_hi;
+      h->layers[i].gp.out_lo = h->layers[i + 1].in_lo;
+    }
+  }
+  if (st != AAE_OK) { tc_decoder_destroy(h); return st; }
+  *out = h;
+  return AAE_OK;
+}
+
+void tc_decoder_destroy(TcDecoder* h) {
+  if (!h) return;
+  for (auto& T : h->layers) { cudaFree(T.in_hi); cudaFree(T.in_lo); cudaFree(T.w_hi); cudaFree(T.w_lo); }
+  for (auto b : h->bias_dev) cudaFree(b);
+  cudaFree(h->wm_tmp);
+  delete h;
+}
+
+// layer 0: dense_1 kernel [latent, h0*w0*f0]; layers 1..L: conv kernels HWIO [5,5,cin,cout]; biases in the reference layout
+int tc_decoder_pack_weights(TcDecoder* h, int layer, const float* w_dev, const float* b_dev, cudaStream_t s) {
+  AAE_REQUIRE(layer >= 0 && layer < (int)h->layers.size(), "tc decoder pack: layer %d out of range", layer);
+  TcLayer& T = h->layers[layer];
+  dim3 block(32, 8);
+  if (layer == 0) {
+    if (w_dev) {
+      dim3 grid((unsigned)ceil_div(T.out_c, 32), (unsigned)ceil_div(T.in_c, 32), 1);
+      pack_weights_kernel<<<grid, block, 0, s>>>(w_dev, 1, T.in_c, T.out_c, W_SCALE, T.w_hi, T.w_lo);
+      AAE_LAUNCH_OK();
+    }
+    if (b_dev) T.gp.bias = b_dev;      // device pointer owned by the decoder handle
+    return AAE_OK;
+  }
+  if (w_dev) {
+    AAE_TRY(launch_merge_subpixel_weights(w_dev, T.in_c, T.out_c, h->wm_tmp, s));
+    dim3 grid((unsigned)ceil_div(4 * T.out_c, 32), (unsigned)ceil_div(T.in_c, 32), 9);
+    pack_weights_kernel<<<grid, block, 0, s>>>(h->wm_tmp, 9, T.in_c, 4 * T.out_c, W_SCALE, T.w_hi, T.w_lo);
+    AAE_LAUNCH_OK();
+  }
+  if (b_dev) {
+    const int n_pad = std::max(T.gp.N, 32);
+    tile_bias_kernel<<<(unsigned)ceil_div(n_pad, 128), 128, 0, s>>>(b_dev, T.out_c, n_pad, h->bias_dev[layer]);
+    AAE_LAUNCH_OK();
+    T.gp.bias = h->bias_dev[layer];
+  }
+  return AAE_OK;
+}
+
+int tc_decoder_forward(TcDecoder* h, const float* z_dev, int B, float* x_out, cudaStream_t s) {
+  TcLayer& D = h->layers[0];
+  split_scale_kernel<<<(unsigned)std::min<int64_t>(1024, ceil_div((int64_t)B * D.in_c, 256)), 256, 0, s>>>(z_dev, (long long)B * D.in_c, ACT_SCALE,
+                                                                                                          D.in_hi, D.in_lo);
+  AAE_LAUNCH_OK();
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    TcLayer& T = h->layers[i];
+    T.gp.M = i == 0 ? B : B * T.in_h * T.in_w;
+    if (i + 1 == h->layers.size()) T.gp.out_f32 = x_out;
+    dim3 grid((unsigned)ceil_div(T.gp.M, 128), (unsigned)ceil_div(T.gp.N, T.n_tile), 1u);
+    if (T.pair) AAE_TRY((launch_tc_gemm2<6, 32>(T, grid, s)));
+    else if (T.n_tile == 256) AAE_TRY((launch_tc_gemm<256, 4, 32>(T, grid, s)));
+    else AAE_TRY((launch_tc_gemm<32, 6, 32>(T, grid, s)));
+  }
   return AAE_OK;
 }
 

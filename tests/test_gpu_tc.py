@@ -132,3 +132,26 @@ def test_c_abi_rejects_bad_calls_without_crashing(sess):
     assert lib.aae_codebook_destroy(cbh) == 0
     assert lib.aae_encoder_forward_u8(h, _lib.ptr(x), 4, _lib.ptr(z), None) == 0                          # handle still healthy
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("batch", [1, 3, 64])
+def test_tc_decoder_forward_matches_oracle(sess, batch):
+    """Decoder.x on the tensor cores (sub-pixel GEMMs, split-fp16) against the float64 oracle and the fp32 SIMT path."""
+    from augmentedautoencoder_b200.ae.decoder import Decoder
+    from augmentedautoencoder_b200.ae.session import placeholder
+    dp = O.make_decoder_params(43, bias_scale=0.05)
+    z = (np.random.RandomState(batch).standard_normal((batch, 128)) * 2.0).astype(np.float32)
+    outs = []
+    for prec in (0, 1):
+        zin = placeholder(np.float32, [None, 128])
+        dec = Decoder(placeholder(np.float32, [None, 128, 128, 3]), zin, list(reversed(O.NUM_FILTER)), 5, list(reversed(O.STRIDES)), "L2", 4,
+                      False, False, max_batch=64, precision=prec)
+        dec.load_weights(dp)
+        outs.append(dec.decode_device(torch.from_numpy(z).cuda()).cpu().numpy())
+    tp = {k: torch.from_numpy(v).double() for k, v in dp.items()}
+    with torch.no_grad():
+        ref = O.decoder_layers(torch.from_numpy(z).double(), tp)[-1].numpy()
+    assert outs[1].shape == ref.shape == (batch, 128, 128, 3)
+    e_simt, e_tc = np.max(np.abs(outs[0] - ref)), np.max(np.abs(outs[1] - ref))
+    print("decoder forward max abs error vs float64: simt %.2e  tc %.2e" % (e_simt, e_tc))
+    assert e_simt < 2e-6 and e_tc < 5e-6
