@@ -22,6 +22,7 @@ class Codebook(object):
         self._encoder = encoder
         self._dataset = dataset
         self.embed_bb = embed_bb
+        self._explicit_precision = precision is not None
         self.precision = encoder.precision if precision is None else int(precision)
         self.max_batch = int(max_batch or encoder.max_batch)
 
@@ -62,8 +63,14 @@ class Codebook(object):
             E = np.ascontiguousarray(self.embedding_normalized.value(), dtype=np.float32)
             h = C.c_void_p()
             with torch.cuda.device(dev):
-                _lib.check(_lib.lib().aae_codebook_create(dev, _lib.ptr(E), E.shape[0], E.shape[1], self.num_cyclo, 0, self.max_batch,
-                                                          self.precision, C.byref(h)), "codebook create")
+                self._encoder.handle(dev)                       # settles the encoder's (possibly automatic) precision first
+                prec = self.precision if self._explicit_precision else self._encoder.precision
+                st = _lib.lib().aae_codebook_create(dev, _lib.ptr(E), E.shape[0], E.shape[1], self.num_cyclo, 0, self.max_batch, prec, C.byref(h))
+                if st == -3 and not self._explicit_precision and prec == _lib.PREC_TC_SPLIT:   # e.g. latent != 128: fp32 CUDA-core match
+                    prec = _lib.PREC_FP32_SIMT
+                    st = _lib.lib().aae_codebook_create(dev, _lib.ptr(E), E.shape[0], E.shape[1], self.num_cyclo, 0, self.max_batch, prec, C.byref(h))
+                _lib.check(st, "codebook create")
+                self.precision = prec
             self._handles[dev] = (h, self._version)
         return self._handles[dev][0]
 

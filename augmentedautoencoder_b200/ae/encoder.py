@@ -96,7 +96,15 @@ class _DeviceModule:
         if dev not in self._handles:
             cfg = _lib.make_cfg(*self._cfg_args)
             h = C.c_void_p()
-            _lib.check(self._create(dev, C.byref(cfg), C.byref(h)), type(self).__name__ + " create")
+            st = self._create(dev, C.byref(cfg), C.byref(h))
+            if st == -3 and getattr(self, "_auto_precision", False) and cfg.precision == _lib.PREC_TC_SPLIT:
+                # geometry outside what the tensor-core kernels are built for (e.g. a toy network): both paths are this
+                # library's CUDA kernels, the fp32 CUDA-core one handles every geometry
+                self.precision = _lib.PREC_FP32_SIMT
+                self._cfg_args = self._cfg_args[:-1] + (self.precision,)
+                cfg = _lib.make_cfg(*self._cfg_args)
+                st = self._create(dev, C.byref(cfg), C.byref(h))
+            _lib.check(st, type(self).__name__ + " create")
             self._handles[dev] = h
             self._upload(dev, h)
         return self._handles[dev]
@@ -134,8 +142,10 @@ class Encoder(_DeviceModule):
         h, w, c = shape[1:]
         self._in_shape = (h, w, c)
         self.max_batch = int(max_batch)
+        # default: tensor cores for inference (fp32-grade split-fp16 arithmetic), the fp32 CUDA-core path for training
+        self._auto_precision = precision is None
         if precision is None:
-            precision = _lib.PREC_FP32_SIMT
+            precision = _lib.PREC_FP32_SIMT if is_training else _lib.PREC_TC_SPLIT
         self.precision = int(precision)
         var_shapes = []
         cin, hh, ww = c, h, w

@@ -207,6 +207,7 @@ struct aae_trainer {
   DevBuf bias_scratch;  // 256 * max(out_c)
   DevBuf sample_sums, z, dz, rec;
   DevBuf dwm;           // gradient wrt merged sub-pixel weights
+  TcTrainPlan* tc = nullptr;  // tensor-core backward plan (encoder and decoder created with AAE_PREC_TC_SPLIT)
 };
 
 // ============================================================================ misc
@@ -673,7 +674,7 @@ extern "C" int aae_trainer_create(aae_encoder* enc, aae_decoder* dec, int bootst
   *out = nullptr;
   AAE_REQUIRE(enc && dec, "null handle");
   AAE_REQUIRE(enc->device == dec->device, "encoder and decoder live on different devices");
-  AAE_REQUIRE(enc->tc == nullptr && dec->tc == nullptr, "training runs on the AAE_PREC_FP32_SIMT encoder / decoder path");
+  AAE_REQUIRE((enc->tc == nullptr) == (dec->tc == nullptr), "encoder and decoder must use the same aae_precision for training");
   AAE_REQUIRE(enc->cfg.max_batch == dec->cfg.max_batch && enc->cfg.in_h == dec->cfg.in_h, "encoder/decoder geometry mismatch");
   DeviceGuard g(enc->device);
   aae_trainer* h = new (std::nothrow) aae_trainer();
@@ -713,6 +714,7 @@ extern "C" int aae_trainer_create(aae_encoder* enc, aae_decoder* dec, int bootst
   if (st == AAE_OK) st = h->z.alloc(B * enc->cfg.latent);
   if (st == AAE_OK) st = h->dz.alloc(B * enc->cfg.latent);
   if (st == AAE_OK && max_wm) st = h->dwm.alloc(max_wm);
+  if (st == AAE_OK && enc->tc) st = tc_train_create(enc->tc, dec->tc, enc->cfg.max_batch, &h->tc);
   if (st != AAE_OK) { aae_trainer_destroy(h); return st; }
   *out = h;
   return AAE_OK;
@@ -725,6 +727,7 @@ extern "C" int aae_trainer_destroy(aae_trainer* h) {
     for (auto& pg : *v) { pg.g.release(); pg.m.release(); pg.v.release(); }
   h->dx_out.release(); h->grad_a.release(); h->grad_b.release(); h->dxup.release(); h->wt.release(); h->partials.release();
   h->bias_scratch.release(); h->sample_sums.release(); h->z.release(); h->dz.release(); h->rec.release(); h->dwm.release();
+  tc_train_destroy(h->tc);
   delete h;
   return AAE_OK;
 }
@@ -763,7 +766,104 @@ static int conv_dgrad(aae_trainer* h, const ConvLayer& L, int B, const float* dy
   return run_igemm(p, GATHER_DGRAD, h->partials, dx, nullptr, ACT_NONE, relu_mask, s);
 }
 
+// dense_1 of the decoder: dy = pre-activation gradient [B, h0*w0*f0] -> bias / kernel gradients and dz
+static int decoder_dense_backward(aae_trainer* h, const float* dy, int B, cudaStream_t s) {
+  aae_decoder* D = h->dec;
+  const int dense_out = D->h0 * D->w0 * D->f0, J = D->cfg.latent;
+  AAE_TRY(launch_bias_grad(dy, B, dense_out, h->dec_b[0].g.p, h->bias_scratch.p, s));
+  IGemmParams p = dense_params(h->z.p, B, J, dy, dense_out);  // WGRAD: src = z, "pixels" = B
+  p.K = B; p.M = J;
+  AAE_TRY(run_igemm(p, GATHER_WGRAD, h->partials, h->dec_k[0].g.p, nullptr, ACT_NONE, nullptr, s));
+  AAE_TRY(launch_transpose_last2(D->dense_w.p, h->wt.p, 1, J, dense_out, s));  // [dense_out, J]
+  IGemmParams q = dense_params(dy, B, dense_out, h->wt.p, J);
+  return run_igemm(q, GATHER_FWD, h->partials, h->dz.p, nullptr, ACT_NONE, nullptr, s);
+}
+
+// dense layer of the encoder: dz -> bias / kernel gradients and the gradient wrt the flattened activation `flat` (fp32,
+// [B, flat]) masked by its ReLU, written to da_out
+static int encoder_dense_backward(aae_trainer* h, const float* flat, int B, float* da_out, cudaStream_t s) {
+  aae_encoder* E = h->enc;
+  const int J = E->cfg.latent, nl = (int)E->conv.size();
+  AAE_TRY(launch_bias_grad(h->dz.p, B, J, h->enc_b[nl].g.p, h->bias_scratch.p, s));
+  IGemmParams p = dense_params(flat, B, E->flat, h->dz.p, J);  // WGRAD: dW[flat, J]
+  p.K = B; p.M = E->flat;
+  AAE_TRY(run_igemm(p, GATHER_WGRAD, h->partials, h->enc_k[nl].g.p, nullptr, ACT_NONE, nullptr, s));
+  AAE_TRY(launch_transpose_last2(E->dense_w.p, h->wt.p, 1, E->flat, J, s));  // [J, flat]
+  IGemmParams q = dense_params(h->dz.p, B, J, h->wt.p, E->flat);
+  return run_igemm(q, GATHER_FWD, h->partials, da_out, nullptr, ACT_NONE, flat, s);  // masked by the ReLU of the last conv
+}
+
+// Training step on the tensor cores: forward through the split-fp16 plans (their (hi, lo) activations double as the ReLU
+// masks and the wgrad operands), conv backward as tcgen05 GEMMs (tc_train.cu), the two dense layers, conv1's wgrad (K = 75)
+// and the elementwise pieces on the fp32 kernels.
+static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, int B, float* loss_out, cudaStream_t s) {
+  aae_encoder* E = h->enc;
+  aae_decoder* D = h->dec;
+  TcTrainPlan* P = h->tc;
+  const int H = E->cfg.in_h, W = E->cfg.in_w, C = E->cfg.in_c;
+  const int numel = H * W * C;
+  const int nl = (int)E->conv.size(), nd = (int)D->conv.size();
+  const int n_units = tc_train_num_units(P), n_dec = tc_train_num_decoder_units(P);
+  AAE_REQUIRE(n_dec == nd && n_units == nd + nl - 1, "tensor-core trainer: plan does not match the network");
+  // ---- operands follow the fp32 master weights (Adam updates those) ----
+  for (int i = 0; i < nl; ++i) AAE_TRY(tc_encoder_pack_weights(E->tc, i, E->conv[i].w.p, s));
+  AAE_TRY(tc_encoder_pack_weights(E->tc, nl, E->dense_w.p, s));
+  AAE_TRY(tc_decoder_pack_weights(D->tc, 0, D->dense_w.p, D->dense_b.p, s));
+  for (int l = 1; l <= nd; ++l) AAE_TRY(tc_decoder_pack_weights(D->tc, l, D->conv[l - 1].w.p, D->conv[l - 1].b.p, s));
+  for (int u = 0; u < n_dec; ++u) AAE_TRY(tc_train_pack_weights(P, u, D->conv[nd - 1 - u].w.p, s));
+  for (int u = n_dec; u < n_units; ++u) AAE_TRY(tc_train_pack_weights(P, u, E->conv[nl - 1 - (u - n_dec)].w.p, s));
+  AAE_TRY(tc_train_begin_step(P, s));
+  // ---- forward ----
+  E->last_batch = B; E->last_was_tc = true;
+  AAE_TRY(tc_encoder_forward(E->tc, x, 0, B, E->conv[0].w.p, E->conv[0].b.p, E->dense_b.p, h->z.p, s));
+  D->last_batch = B;
+  AAE_TRY(tc_decoder_forward(D->tc, h->z.p, B, h->rec.p, s));
+  const int k = h->bootstrap_ratio > 1 ? numel / h->bootstrap_ratio : numel;
+  AAE_TRY(launch_bootstrap_l2(h->rec.p, y, B, numel, k, h->sample_sums.p, loss_out, h->dx_out.p, s));
+  AAE_TRY(launch_sigmoid_grad(h->dx_out.p, h->rec.p, (int64_t)B * numel, s));
+  // ---- decoder backward ----
+  AAE_TRY(launch_bias_grad(h->dx_out.p, (int64_t)B * H * W, C, h->dec_b[nd].g.p, h->bias_scratch.p, s));
+  AAE_TRY(tc_train_set_loss_grad(P, h->dx_out.p, B, s));
+  float* raw = tc_train_raw(P);
+  for (int u = 0; u < n_dec; ++u) {
+    const int l = nd - u;                        // decoder conv layer l (1-based; dec_k[l], D->conv[l-1])
+    int is_enc, cin, cout, gh, gw, ndc;
+    tc_train_unit_info(P, u, &is_enc, &cin, &cout, &gh, &gw, &ndc);
+    AAE_TRY(tc_train_unit_wgrad(P, u, B, h->dwm.p, s));
+    AAE_TRY(launch_unmerge_subpixel_grads(h->dwm.p, cin, cout, h->dec_k[l].g.p, s));
+    AAE_TRY(tc_train_unit_dgrad(P, u, B, s));
+    AAE_TRY(tc_train_finish(P, u, u + 1 < n_dec ? u + 1 : -1, B, false, s));
+    // raw is now the masked pre-activation gradient of the producing layer (conv l-1, or dense_1): its bias gradient
+    if (l > 1) AAE_TRY(launch_bias_grad(raw, (int64_t)B * gh * gw, cin, h->dec_b[l - 1].g.p, h->bias_scratch.p, s));
+  }
+  AAE_TRY(decoder_dense_backward(h, raw, B, s));
+  // ---- encoder backward ----
+  float* flat = E->conv.back().out.p;            // fp32 view of the last conv activation for the fp32 dense backward
+  AAE_TRY(tc_train_unpack_flat(P, B, flat, s));
+  float* da = h->grad_a.p;
+  AAE_TRY(encoder_dense_backward(h, flat, B, da, s));
+  {
+    const ConvLayer& L = E->conv.back();
+    AAE_TRY(launch_bias_grad(da, (int64_t)B * L.out_h * L.out_w, L.out_c, h->enc_b[nl - 1].g.p, h->bias_scratch.p, s));
+    AAE_TRY(tc_train_set_unit_grad(P, n_dec, da, B, s));
+  }
+  for (int u = n_dec; u < n_units; ++u) {
+    const int i = nl - 1 - (u - n_dec);          // encoder conv index (E->conv[i], enc_k[i]); i >= 1
+    int is_enc, cin, cout, gh, gw, ndc;
+    tc_train_unit_info(P, u, &is_enc, &cin, &cout, &gh, &gw, &ndc);
+    AAE_TRY(tc_train_unit_wgrad(P, u, B, h->enc_k[i].g.p, s));
+    AAE_TRY(tc_train_unit_dgrad(P, u, B, s));
+    const bool last = u + 1 == n_units;
+    AAE_TRY(tc_train_finish(P, u, last ? -1 : u + 1, B, last, s));
+    // masked gradient of conv i-1's output, space-to-depth order [pixels/4][(cls, cin)] = [pixels][cin] rows for the column sum
+    AAE_TRY(launch_bias_grad(raw, (int64_t)B * gh * gw * 4, cin, h->enc_b[i - 1].g.p, h->bias_scratch.p, s));
+  }
+  // conv1 (Cin = 3, K = 75): fp32 wgrad from the plain-layout gradient the last unit wrote
+  return conv_wgrad(h, E->conv[0], x, B, tc_train_f32_out(P), h->enc_k[0].g.p, s);
+}
+
 static int trainer_fwd_bwd(aae_trainer* h, const float* x, const float* y, int B, float* loss_out, cudaStream_t s) {
+  if (h->tc) return trainer_fwd_bwd_tc(h, x, y, B, loss_out, s);
   aae_encoder* E = h->enc;
   aae_decoder* D = h->dec;
   const int H = E->cfg.in_h, W = E->cfg.in_w, C = E->cfg.in_c;
@@ -815,27 +915,11 @@ static int trainer_fwd_bwd(aae_trainer* h, const float* x, const float* y, int B
     dy = ping;
     std::swap(ping, pong);
   }
-  {  // dense_1: dy is [B, h0*w0*f0] (pre-activation gradient)
-    const int dense_out = D->h0 * D->w0 * D->f0, J = D->cfg.latent;
-    AAE_TRY(launch_bias_grad(dy, B, dense_out, h->dec_b[0].g.p, h->bias_scratch.p, s));
-    IGemmParams p = dense_params(h->z.p, B, J, dy, dense_out);  // WGRAD: src = z, "pixels" = B
-    p.K = B; p.M = J;
-    AAE_TRY(run_igemm(p, GATHER_WGRAD, h->partials, h->dec_k[0].g.p, nullptr, ACT_NONE, nullptr, s));
-    AAE_TRY(launch_transpose_last2(D->dense_w.p, h->wt.p, 1, J, dense_out, s));  // [dense_out, J]
-    IGemmParams q = dense_params(dy, B, dense_out, h->wt.p, J);
-    AAE_TRY(run_igemm(q, GATHER_FWD, h->partials, h->dz.p, nullptr, ACT_NONE, nullptr, s));
-  }
+  AAE_TRY(decoder_dense_backward(h, dy, B, s));
   // ---- encoder backward ----
   {
-    const int J = E->cfg.latent, nl = (int)E->conv.size();
-    const float* flat = E->conv.back().out.p;
-    AAE_TRY(launch_bias_grad(h->dz.p, B, J, h->enc_b[nl].g.p, h->bias_scratch.p, s));
-    IGemmParams p = dense_params(flat, B, E->flat, h->dz.p, J);  // WGRAD: dW[flat, J]
-    p.K = B; p.M = E->flat;
-    AAE_TRY(run_igemm(p, GATHER_WGRAD, h->partials, h->enc_k[nl].g.p, nullptr, ACT_NONE, nullptr, s));
-    AAE_TRY(launch_transpose_last2(E->dense_w.p, h->wt.p, 1, E->flat, J, s));  // [J, flat]
-    IGemmParams q = dense_params(h->dz.p, B, J, h->wt.p, E->flat);
-    AAE_TRY(run_igemm(q, GATHER_FWD, h->partials, ping, nullptr, ACT_NONE, flat, s));  // masked by ReLU of the last conv
+    const int nl = (int)E->conv.size();
+    AAE_TRY(encoder_dense_backward(h, E->conv.back().out.p, B, ping, s));
     dy = ping;
     std::swap(ping, pong);
     for (int i = nl - 1; i >= 0; --i) {

@@ -33,6 +33,24 @@ void tc_decoder_destroy(TcDecoder* h);
 int tc_decoder_pack_weights(TcDecoder* h, int layer, const float* w_dev, const float* b_dev, cudaStream_t s);
 int tc_decoder_forward(TcDecoder* h, const float* z_dev, int B, float* x_out, cudaStream_t s);
 
+// ---- training: backward GEMMs (tc_train.cu); units are the conv layers in backward order (decoder L..1, encoder L..2)
+struct TcTrainPlan;
+int tc_train_create(TcEncoder* enc, TcDecoder* dec, int max_batch, TcTrainPlan** out);
+void tc_train_destroy(TcTrainPlan* h);
+int tc_train_num_units(const TcTrainPlan* h);
+int tc_train_num_decoder_units(const TcTrainPlan* h);
+void tc_train_unit_info(const TcTrainPlan* h, int u, int* is_enc, int* cin, int* cout, int* gh, int* gw, int* nd);
+float* tc_train_raw(TcTrainPlan* h);
+float* tc_train_f32_out(TcTrainPlan* h);
+int tc_train_begin_step(TcTrainPlan* h, cudaStream_t s);
+int tc_train_pack_weights(TcTrainPlan* h, int u, const float* w_dev, cudaStream_t s);
+int tc_train_set_loss_grad(TcTrainPlan* h, const float* g_dev, int B, cudaStream_t s);
+int tc_train_set_unit_grad(TcTrainPlan* h, int u, const float* g_dev, int B, cudaStream_t s);
+int tc_train_unit_wgrad(TcTrainPlan* h, int u, int B, float* dw_out, cudaStream_t s);
+int tc_train_unit_dgrad(TcTrainPlan* h, int u, int B, cudaStream_t s);
+int tc_train_finish(TcTrainPlan* h, int u, int next, int B, bool want_f32, cudaStream_t s);
+int tc_train_unpack_flat(TcTrainPlan* h, int B, float* out, cudaStream_t s);
+
 int tc_codebook_create(int device, const float* E_dev, int64_t n_rows, int latent, int max_batch, TcCodebook** out);
 void tc_codebook_destroy(TcCodebook* h);
 int tc_codebook_match(TcCodebook* h, const float* E_dev, const float* z_dev, int B, int64_t row_offset, int num_cyclo, int upright,

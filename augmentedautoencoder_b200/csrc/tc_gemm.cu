@@ -24,6 +24,7 @@
 
 #include "tc.cuh"
 #include "tc_common.cuh"
+#include "tc_plan.cuh"
 
 namespace aae {
 
@@ -58,104 +59,6 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 }
 
 // ------------------------------------------------------------------------------------------------- kernel
-enum TcOutMode : int {
-  OUT_S2D_SPLIT = 0,      // (hi, lo) fp16, space-to-depth layout of the next stride-2 conv
-  OUT_PLAIN_SPLIT = 1,    // (hi, lo) fp16, plain [M, N]
-  OUT_F32 = 2,            // fp32 [splits, M, N] raw accumulators (split-K partials)
-  OUT_D2S_SPLIT = 3,      // (hi, lo) fp16, depth-to-space: column (cls, co) of pixel (b,i,j) -> pixel (2i+py, 2j+px) of [B,2OH,2OW,N/4]
-  OUT_D2S_F32 = 4         // fp32, depth-to-space with `cout_real` channels per parity (decoder output layer, N padded)
-};
-
-struct TcGemmParams {
-  int M;                 // valid output rows (pixels, or batch rows for the dense layer)
-  int N;                 // total output channels
-  int OH, OW;            // output spatial dims (1,1 for dense)
-  int BW, BH;            // pixel box of one 128-row tile: BW*BH*BB = 128
-  int taps;              // 25 (conv) or 1 (dense)
-  int chunks_per_tap;    // Cin / 64
-  int iters_per_split;   // K iterations (tap, chunk) handled per blockIdx.z
-  int8_t tap_di[32], tap_dj[32];
-  int tap_ch[32];        // channel offset of the tap's parity plane in the space-to-depth tensor
-  float unscale;         // 1 / (scale_A * scale_W)
-  float out_scale;       // scale applied before the hi/lo split of the output (next layer's scale_A)
-  const float* bias;
-  int relu;              // activation: 0 none, 1 ReLU, 2 sigmoid
-  int cout_real;         // OUT_D2S_F32: real channels per parity class (columns >= 4*cout_real are padding)
-  int out_mode;
-  __half* out_hi;
-  __half* out_lo;
-  float* out_f32;        // OUT_F32: [splits, M, N]
-};
-
-
-// ------------------------------------------------------------------------------------------------- shared epilogue
-struct TcRow {
-  bool valid;
-  int b, i, j;            // pixel coordinates on the OH x OW grid
-  long long row_off;      // element offset of column 0 for the row-contiguous output modes
-};
-
-__device__ __forceinline__ TcRow tc_decode_row(const TcGemmParams& p, int m) {
-  TcRow r;
-  r.valid = m < p.M;
-  r.b = r.i = r.j = 0;
-  r.row_off = 0;
-  if (!r.valid) return r;
-  const int hw = p.OH * p.OW;
-  r.b = m / hw;
-  const int rem = m - r.b * hw;
-  r.i = rem / p.OW;
-  r.j = rem - r.i * p.OW;
-  if (p.out_mode == OUT_S2D_SPLIT)
-    r.row_off = ((long long)(r.b * (p.OH >> 1) + (r.i >> 1)) * (p.OW >> 1) + (r.j >> 1)) * (4LL * p.N) + (((r.i & 1) << 1) | (r.j & 1)) * p.N;
-  else
-    r.row_off = (long long)m * p.N;
-  return r;
-}
-
-// f[0..31]: accumulator values (already hh + cross, times unscale) of columns n .. n+31 of this thread's row
-__device__ __forceinline__ void tc_store_chunk(const TcGemmParams& p, const TcRow& r, int n, float (&f)[32], int split_z) {
-  if (p.out_mode == OUT_F32) {
-    float* dst = p.out_f32 + (long long)split_z * p.M * p.N + r.row_off + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-    return;
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float a = f[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-    if (p.relu == 1) a = fmaxf(a, 0.f);
-    else if (p.relu == 2) a = 1.f / (1.f + expf(-a));
-    f[j] = a;
-  }
-  if (p.out_mode == OUT_D2S_F32) {
-    const int cr = p.cout_real;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int nn = n + j;
-      if (nn >= 4 * cr) continue;
-      const int cls = nn / cr, co = nn - cls * cr;
-      p.out_f32[((long long)(r.b * 2 * p.OH + 2 * r.i + (cls >> 1)) * (2 * p.OW) + 2 * r.j + (cls & 1)) * cr + co] = f[j];
-    }
-    return;
-  }
-  long long off = r.row_off + n;
-  if (p.out_mode == OUT_D2S_SPLIT) {
-    const int cq = p.N >> 2, cls = n / cq, co = n - cls * cq;     // a 32-column chunk never straddles a parity class (cq % 32 == 0)
-    off = ((long long)(r.b * 2 * p.OH + 2 * r.i + (cls >> 1)) * (2 * p.OW) + 2 * r.j + (cls & 1)) * cq + co;
-  }
-  uint32_t hi[16], lo[16];
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) split_f16x2(f[j] * p.out_scale, f[j + 1] * p.out_scale, hi[j >> 1], lo[j >> 1]);
-  uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
-  uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-    dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-  }
-}
-
 template <int N_TILE, int STAGES, int KCH = 64>
 struct TcSmem {
   static constexpr int A_BYTES = 128 * KCH * 2;        // 128 rows x KCH fp16
@@ -254,6 +157,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const bool has_work = it_end > it_begin;
+    const float unscale = p.amax_bits ? p.unscale * tc_dyn_unscale(__ldg(p.amax_bits)) : p.unscale;
 #pragma unroll 1
     for (int c = 0; c < N_TILE / 32; ++c) {
       uint32_t v[32], x[32];
@@ -264,7 +168,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       if (!row.valid || n >= p.N) continue;
       float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = has_work ? (__uint_as_float(v[j]) + __uint_as_float(x[j])) * p.unscale : 0.f;
+      for (int j = 0; j < 32; ++j) f[j] = has_work ? (__uint_as_float(v[j]) + __uint_as_float(x[j])) * unscale : 0.f;
       tc_store_chunk(p, row, n, f, (int)blockIdx.z);
     }
   }
@@ -372,6 +276,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const TcRow row = tc_decode_row(p, m0 + q * 32 + lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    const float unscale = p.amax_bits ? p.unscale * tc_dyn_unscale(__ldg(p.amax_bits)) : p.unscale;
 #pragma unroll 1
     for (int c = 0; c < N_TILE / 32; ++c) {
       uint32_t v[32], x[32];
@@ -382,7 +287,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       if (!row.valid || n >= p.N) continue;
       float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * p.unscale;
+      for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * unscale;
       tc_store_chunk(p, row, n, f, 0);
     }
   }
@@ -439,38 +344,6 @@ __global__ void unpack_act_kernel(const __half* __restrict__ hi, const __half* _
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------- encoder plan
-constexpr float ACT_SCALE = 16.f;     // activations (and the [0,1] input) are stored as 16 * x
-constexpr float W_SCALE = 256.f;      // weights are stored as 256 * w
-constexpr int TC_STAGES = 2;
-
-struct TcLayer {
-  int in_h, in_w, in_c, out_h, out_w, out_c;   // conv geometry (input is the space-to-depth tensor [B, in_h/2, in_w/2, 4*in_c])
-  int taps, BW, BH, BB;
-  __half *in_hi = nullptr, *in_lo = nullptr;    // activations entering this layer
-  __half *w_hi = nullptr, *w_lo = nullptr;      // packed weights [out_c][taps*in_c]
-  CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo;
-  CUtensorMap tm_w2_hi, tm_w2_lo;               // weight tile halves (128 rows) for the CTA-pair kernel
-  bool pair = false;
-  TcGemmParams gp;
-  int n_tile;
-  int kch;    // K chunk per pipeline stage: 64 (128-byte swizzle) or 32 (64-byte swizzle, 4 stages)
-};
-
-struct TcEncoder {
-  int device;
-  aae_net_cfg cfg;
-  std::vector<TcLayer> layers;   // conv layers 1..L-1 followed by the dense layer
-  int flat;
-  float* partials = nullptr;     // dense split-K partials [splits, max_batch, latent]
-  int dense_splits = 1;
-  TcConv1* conv1 = nullptr;      // tensor-core first layer (when the geometry allows), else the fp32 SIMT kernel
-  float* dbg = nullptr;          // fp32 view of an activation (tests)
-  size_t dbg_floats = 0;
-  bool timer_on = false;
-  std::vector<cudaEvent_t> ev;
-  int ev_used = 0;
-};
-
 namespace {
 
 template <int STAGES, int KCH>
@@ -494,16 +367,30 @@ int launch_tc_gemm(const TcLayer& L, dim3 grid, cudaStream_t s) {
   return AAE_OK;
 }
 
-int dev_alloc(void** p, size_t bytes) {
+int dev_alloc(void** p, size_t bytes) { return tc_dev_alloc(p, bytes); }
+
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace
+
+int tc_dev_alloc(void** p, size_t bytes) {
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess) { *p = nullptr; set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return AAE_ERR_OOM; }
   cudaMemset(*p, 0, bytes);
   return AAE_OK;
 }
 
-bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
-
-}  // namespace
+int tc_launch_layer(const TcLayer& T, dim3 grid, cudaStream_t s) {
+  if (T.pair && T.kch == 32) return launch_tc_gemm2<6, 32>(T, grid, s);
+  if (T.pair) return launch_tc_gemm2<3, 64>(T, grid, s);
+  if (T.n_tile == 256 && T.kch == 32) return launch_tc_gemm<256, 4, 32>(T, grid, s);
+  if (T.n_tile == 256) return launch_tc_gemm<256, TC_STAGES, 64>(T, grid, s);
+  if (T.n_tile == 128 && T.kch == 64) return launch_tc_gemm<128, 3, 64>(T, grid, s);
+  if (T.n_tile == 128 && T.kch == 32) return launch_tc_gemm<128, 6, 32>(T, grid, s);
+  if (T.n_tile == 32 && T.kch == 32) return launch_tc_gemm<32, 6, 32>(T, grid, s);
+  set_error("tc_launch_layer: no kernel for n_tile=%d kch=%d", T.n_tile, T.kch);
+  return AAE_ERR_UNSUPPORTED;
+}
 
 int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
   *out = nullptr;
@@ -689,11 +576,7 @@ int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const
     const bool dense = (i + 1 == h->layers.size());
     T.gp.M = dense ? B : B * T.out_h * T.out_w;
     dim3 grid((unsigned)ceil_div(T.gp.M, 128), (unsigned)ceil_div(T.out_c, T.n_tile), dense ? (unsigned)h->dense_splits : 1u);
-    if (T.pair && T.kch == 32) AAE_TRY((launch_tc_gemm2<6, 32>(T, grid, s)));
-    else if (T.pair) AAE_TRY((launch_tc_gemm2<3, 64>(T, grid, s)));
-    else if (T.n_tile == 256 && T.kch == 32) AAE_TRY((launch_tc_gemm<256, 4, 32>(T, grid, s)));
-    else if (T.n_tile == 256) AAE_TRY((launch_tc_gemm<256, TC_STAGES, 64>(T, grid, s)));
-    else AAE_TRY((launch_tc_gemm<128, 3, 64>(T, grid, s)));
+    AAE_TRY(tc_launch_layer(T, grid, s));
     if (dense) AAE_TRY(launch_splitk_reduce(h->partials, h->dense_splits, (int64_t)B * cfg.latent, cfg.latent, dense_b, ACT_NONE, z_out, s));
     tc_mark(h, s);
   }
@@ -753,21 +636,14 @@ __global__ void tile_bias_kernel(const float* __restrict__ b, int cout, int n_pa
 
 }  // namespace
 
-struct TcDecoder {
-  int device;
-  aae_net_cfg cfg;
-  std::vector<TcLayer> layers;     // [0] dense_1, [1..L-1] sub-pixel convs, [L] sub-pixel output layer
-  std::vector<float*> bias_dev;    // per layer: bias in GEMM-column order (dense: the caller's; convs: tiled 4x, padded)
-  float* wm_tmp = nullptr;         // fp32 merged-weight scratch
-  size_t wm_floats = 0;
-};
-
-static int tc_layer_alloc_common(TcLayer& T, int B, bool pair_ok) {
+int tc_layer_setup_plain(TcLayer& T, int B, bool pair_ok, bool alloc_input) {
   int st;
   const int B_pad = (int)ceil_div(B, T.BB) * T.BB;
   const size_t act = (size_t)B_pad * T.in_h * T.in_w * T.in_c;
-  if ((st = dev_alloc((void**)&T.in_hi, act * sizeof(__half))) != AAE_OK) return st;
-  if ((st = dev_alloc((void**)&T.in_lo, act * sizeof(__half))) != AAE_OK) return st;
+  if (alloc_input) {
+    if ((st = dev_alloc((void**)&T.in_hi, act * sizeof(__half))) != AAE_OK) return st;
+    if ((st = dev_alloc((void**)&T.in_lo, act * sizeof(__half))) != AAE_OK) return st;
+  }
   const uint64_t K = (uint64_t)T.taps * T.in_c;
   const int rows = (int)ceil_div(T.gp.N, T.n_tile) * T.n_tile;
   if ((st = dev_alloc((void**)&T.w_hi, (size_t)rows * K * sizeof(__half))) != AAE_OK) return st;
@@ -843,7 +719,7 @@ int tc_decoder_create(int device, const aae_net_cfg* cfg, TcDecoder** out) {
     }
     g.unscale = 1.f / (ACT_SCALE * W_SCALE);
     g.out_scale = ACT_SCALE;
-    if ((st = tc_layer_alloc_common(T, B, /*pair_ok=*/l > 0)) != AAE_OK) { h->layers.push_back(T); break; }
+    if ((st = tc_layer_setup_plain(T, B, /*pair_ok=*/l > 0, /*alloc_input=*/true)) != AAE_OK) { h->layers.push_back(T); break; }
     h->layers.push_back(T);
     float* bz = nullptr;
     if (l > 0) st = dev_alloc((void**)&bz, (size_t)std::max(g.N, 32) * sizeof(float));
@@ -909,9 +785,7 @@ int tc_decoder_forward(TcDecoder* h, const float* z_dev, int B, float* x_out, cu
     T.gp.M = i == 0 ? B : B * T.in_h * T.in_w;
     if (i + 1 == h->layers.size()) T.gp.out_f32 = x_out;
     dim3 grid((unsigned)ceil_div(T.gp.M, 128), (unsigned)ceil_div(T.gp.N, T.n_tile), 1u);
-    if (T.pair) AAE_TRY((launch_tc_gemm2<6, 32>(T, grid, s)));
-    else if (T.n_tile == 256) AAE_TRY((launch_tc_gemm<256, 4, 32>(T, grid, s)));
-    else AAE_TRY((launch_tc_gemm<32, 6, 32>(T, grid, s)));
+    AAE_TRY(tc_launch_layer(T, grid, s));
   }
   return AAE_OK;
 }
