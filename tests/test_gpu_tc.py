@@ -155,3 +155,53 @@ def test_tc_decoder_forward_matches_oracle(sess, batch):
     e_simt, e_tc = np.max(np.abs(outs[0] - ref)), np.max(np.abs(outs[1] - ref))
     print("decoder forward max abs error vs float64: simt %.2e  tc %.2e" % (e_simt, e_tc))
     assert e_simt < 2e-6 and e_tc < 5e-6
+
+
+def _train_pair(prec, B):
+    from augmentedautoencoder_b200.ae.ae import AE
+    from augmentedautoencoder_b200.ae.ae_factory import TrainOp
+    from augmentedautoencoder_b200.ae.decoder import Decoder
+    from augmentedautoencoder_b200.ae.encoder import Encoder
+    from augmentedautoencoder_b200.ae.session import placeholder
+    x = placeholder(np.float32, [None, 128, 128, 3])
+    y = placeholder(np.float32, [None, 128, 128, 3])
+    enc = Encoder(x, 128, list(O.NUM_FILTER), 5, list(O.STRIDES), False, is_training=True, max_batch=B, precision=prec)
+    dec = Decoder(y, enc.z, list(reversed(O.NUM_FILTER)), 5, list(reversed(O.STRIDES)), "L2", 4, False, False, is_training=True, max_batch=B,
+                  precision=prec)
+    ep, dp = O.make_encoder_params(42, bias_scale=0.02), O.make_decoder_params(43, bias_scale=0.02)
+    enc.load_weights(ep)
+    dec.load_weights(dp)
+    return enc, dec, TrainOp(AE(enc, dec, 0, 0), 2e-4), ep, dp
+
+
+def test_tc_training_gradients_match_float64_oracle(sess):
+    """Tensor-core trainer (tcgen05 forward, dgrad and wgrad GEMMs): loss and all 20 gradients of one forward/backward vs the
+    float64 oracle.  Compared in relative L2 norm: a ReLU unit whose pre-activation is within the split-fp16 rounding of zero
+    may fall on either side (as in any finite-precision implementation), which perturbs a few entries discretely."""
+    enc, dec, top, ep, dp = _train_pair(1, 2)
+    xb = np.random.RandomState(8).rand(1, 128, 128, 3).astype(np.float32)
+    yb = np.random.RandomState(4).rand(1, 128, 128, 3).astype(np.float32)
+    loss = top.step_device(torch.from_numpy(xb).cuda(), torch.from_numpy(yb).cuda(), update=False)
+    loss64, _, g64 = O.ae_forward_loss(xb, yb, ep, dp, dtype=torch.float64, with_grads=True)
+    assert abs(float(loss) - loss64) < 2e-6 * max(1.0, abs(loss64))
+    grads = top.gradients(sess.device)
+    worst = 0.0
+    for name, gr in g64.items():
+        rel = np.linalg.norm(grads[name].astype(np.float64) - gr) / max(np.linalg.norm(gr), 1e-30)
+        worst = max(worst, rel)
+        assert rel < 3e-4, (name, rel)
+    print("tensor-core trainer: worst relative L2 gradient error vs float64 %.2e" % worst)
+
+
+def test_tc_training_steps_track_the_fp32_trainer(sess):
+    """Five Adam steps at batch 3 (ragged against the 128-row tiles): the loss trajectory of the tensor-core trainer follows
+    the fp32 CUDA-core trainer, and the loss goes down."""
+    xb = torch.from_numpy(np.random.RandomState(11).rand(3, 128, 128, 3).astype(np.float32)).cuda()
+    yb = torch.from_numpy(np.random.RandomState(12).rand(3, 128, 128, 3).astype(np.float32)).cuda()
+    traj = {}
+    for prec in (0, 1):
+        enc, dec, top, _, _ = _train_pair(prec, 4)
+        traj[prec] = [float(top.step_device(xb, yb, update=True)) for _ in range(5)]
+        del enc, dec, top
+    assert traj[1][-1] < traj[1][0]
+    assert np.max(np.abs(np.array(traj[0]) - np.array(traj[1]))) < 2e-4, traj
