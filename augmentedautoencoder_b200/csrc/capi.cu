@@ -736,6 +736,8 @@ extern "C" int64_t aae_trainer_global_step(const aae_trainer* h) { return h ? h-
 
 // wgrad of one conv layer: dW[tap,ci,co] = sum_pix X[pix@tap,ci] dY[pix,co]
 static int conv_wgrad(aae_trainer* h, const ConvLayer& L, const void* src, int B, const float* dy, float* dw, cudaStream_t s) {
+  if (L.ups == 0 && conv1_wgrad_supported(L.in_h, L.in_w, L.in_c, L.out_h, L.out_w, L.out_c, L.ksize, L.stride))
+    return launch_conv1_wgrad((const float*)src, dy, B, L.in_h, L.in_w, L.out_h, L.out_w, L.pad_t, L.pad_l, h->partials.p, h->partials.n, dw, s);
   IGemmParams p = conv_params(L, src, 0, B);
   p.Bm = dy;                       // [pixels, out_c]
   p.K = B * L.out_h * L.out_w;     // reduction over pixels
@@ -809,8 +811,10 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
   for (int i = 0; i < nl; ++i) AAE_TRY(tc_encoder_pack_weights(E->tc, i, E->conv[i].w.p, s));
   AAE_TRY(tc_encoder_pack_weights(E->tc, nl, E->dense_w.p, s));
   AAE_TRY(tc_decoder_pack_weights(D->tc, 0, D->dense_w.p, D->dense_b.p, s));
-  for (int l = 1; l <= nd; ++l) AAE_TRY(tc_decoder_pack_weights(D->tc, l, D->conv[l - 1].w.p, D->conv[l - 1].b.p, s));
-  for (int u = 0; u < n_dec; ++u) AAE_TRY(tc_train_pack_weights(P, u, D->conv[nd - 1 - u].w.p, s));
+  for (int l = 1; l <= nd; ++l) {   // forward and dgrad operands of a decoder layer share one merge of its 5x5 taps
+    AAE_TRY(tc_decoder_pack_weights(D->tc, l, D->conv[l - 1].w.p, D->conv[l - 1].b.p, s));
+    AAE_TRY(tc_train_pack_weights_merged(P, nd - l, tc_decoder_merged_weights(D->tc), s));
+  }
   for (int u = n_dec; u < n_units; ++u) AAE_TRY(tc_train_pack_weights(P, u, E->conv[nl - 1 - (u - n_dec)].w.p, s));
   AAE_TRY(tc_train_begin_step(P, s));
   // ---- forward ----
@@ -832,9 +836,9 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
     AAE_TRY(tc_train_unit_wgrad(P, u, B, h->dwm.p, s));
     AAE_TRY(launch_unmerge_subpixel_grads(h->dwm.p, cin, cout, h->dec_k[l].g.p, s));
     AAE_TRY(tc_train_unit_dgrad(P, u, B, s));
-    AAE_TRY(tc_train_finish(P, u, u + 1 < n_dec ? u + 1 : -1, B, false, s));
-    // raw is now the masked pre-activation gradient of the producing layer (conv l-1, or dense_1): its bias gradient
-    if (l > 1) AAE_TRY(launch_bias_grad(raw, (int64_t)B * gh * gw, cin, h->dec_b[l - 1].g.p, h->bias_scratch.p, s));
+    // masks with the ReLU of the producing layer (conv l-1, or dense_1) and folds that layer's bias gradient into the same pass;
+    // dense_1's fp32 backward reads the masked gradient itself
+    AAE_TRY(tc_train_finish(P, u, u + 1 < n_dec ? u + 1 : -1, B, false, /*keep_masked=*/l == 1, l > 1 ? h->dec_b[l - 1].g.p : nullptr, s));
   }
   AAE_TRY(decoder_dense_backward(h, raw, B, s));
   // ---- encoder backward ----
@@ -854,9 +858,8 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
     AAE_TRY(tc_train_unit_wgrad(P, u, B, h->enc_k[i].g.p, s));
     AAE_TRY(tc_train_unit_dgrad(P, u, B, s));
     const bool last = u + 1 == n_units;
-    AAE_TRY(tc_train_finish(P, u, last ? -1 : u + 1, B, last, s));
-    // masked gradient of conv i-1's output, space-to-depth order [pixels/4][(cls, cin)] = [pixels][cin] rows for the column sum
-    AAE_TRY(launch_bias_grad(raw, (int64_t)B * gh * gw * 4, cin, h->enc_b[i - 1].g.p, h->bias_scratch.p, s));
+    // masked gradient of conv i-1's output (space-to-depth order, columns (cls, cin)); its column sums are conv i-1's bias gradient
+    AAE_TRY(tc_train_finish(P, u, last ? -1 : u + 1, B, last, false, h->enc_b[i - 1].g.p, s));
   }
   // conv1 (Cin = 3, K = 75): fp32 wgrad from the plain-layout gradient the last unit wrote
   return conv_wgrad(h, E->conv[0], x, B, tc_train_f32_out(P), h->enc_k[0].g.p, s);
@@ -959,8 +962,15 @@ extern "C" int aae_train_step(aae_trainer* h, const float* x_dev, const float* y
   h->step += 1;
   const double t = (double)h->step;
   const float lr_t = (float)((double)h->lr * sqrt(1.0 - pow((double)h->b2, t)) / (1.0 - pow((double)h->b1, t)));
+  AdamBatch ab;
+  ab.count = 0;
   for (auto* v : {&h->enc_k, &h->enc_b, &h->dec_k, &h->dec_b})
-    for (auto& pg : *v) AAE_TRY(launch_adam(pg.p, pg.g.p, pg.m.p, pg.v.p, (int64_t)pg.n, lr_t, h->b1, h->b2, h->eps, s));
+    for (auto& pg : *v) {
+      if (ab.count == AdamBatch::kMax) { AAE_TRY(launch_adam_multi(ab, lr_t, h->b1, h->b2, h->eps, s)); ab.count = 0; }
+      const int t = ab.count++;
+      ab.p[t] = pg.p; ab.g[t] = pg.g.p; ab.m[t] = pg.m.p; ab.v[t] = pg.v.p; ab.n[t] = (long long)pg.n;
+    }
+  if (ab.count) AAE_TRY(launch_adam_multi(ab, lr_t, h->b1, h->b2, h->eps, s));
   for (auto& L : h->dec->conv) L.wm_dirty = true;   // the merged sub-pixel weights follow the updated taps
   return AAE_OK;
 }

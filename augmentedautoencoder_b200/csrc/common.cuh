@@ -112,6 +112,18 @@ int launch_mul_mask(float* dy, const float* y, int64_t n, cudaStream_t stream); 
 int launch_sigmoid_grad(float* dx, const float* x, int64_t n, cudaStream_t stream);          // dx *= x (1 - x)
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
                 cudaStream_t stream);
+// the same update for up to kMax tensors in one launch (fill p/g/m/v/n and count; chunk_begin is computed by the launcher)
+struct AdamBatch {
+  static constexpr int kMax = 32;
+  float* p[kMax];
+  const float* g[kMax];
+  float* m[kMax];
+  float* v[kMax];
+  long long n[kMax];
+  int chunk_begin[kMax + 1];
+  int count;
+};
+int launch_adam_multi(AdamBatch& b, float lr_t, float b1, float b2, float eps, cudaStream_t stream);
 // Sub-pixel form of "nearest-neighbour x2 upsample, then conv 5x5 stride 1 SAME" (auto_pose/ae/decoder.py:54-62): the four
 // output parities (py, px) are four 3x3 convolutions of the LOW-resolution input whose taps are sums of the original
 // taps that land on the same source pixel -- 9/25 of the multiply-adds.  W [5,5,ci,co] -> Wm [3,3,ci,(py,px,co)].
@@ -120,6 +132,10 @@ int launch_merge_subpixel_weights(const float* w, int cin, int cout, float* wm, 
 int launch_unmerge_subpixel_grads(const float* dwm, int cin, int cout, float* dw, cudaStream_t stream);
 // plain NHWC [B, 2h, 2w, C] -> space-to-depth [B, h, w, (py, px, c)]
 int launch_space_to_depth(const float* in, float* out, int B, int h, int w, int C, cudaStream_t stream);
+// dedicated wgrad of the first encoder layer (5x5 / stride 2 / Cin 3 / Cout 128): x fp32 NHWC, dy fp32 [B,OH,OW,128] -> dw [75,128]
+bool conv1_wgrad_supported(int H, int W, int C, int OH, int OW, int N, int ksize, int stride);
+int launch_conv1_wgrad(const float* x, const float* dy, int B, int H, int W, int OH, int OW, int pad_t, int pad_l, float* partial,
+                       size_t partial_floats, float* dw, cudaStream_t stream);
 int launch_conv_small_n(const IGemmParams& p, cudaStream_t stream);
 // p.K = number of pixels, p.Bm = dY [pixels, N<=3]; partial: [chunks, taps*SC*N]
 int launch_wgrad_small_n(const IGemmParams& p, int chunks, float* partial, cudaStream_t stream);

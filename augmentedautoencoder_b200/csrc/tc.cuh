@@ -32,6 +32,7 @@ int tc_decoder_create(int device, const aae_net_cfg* cfg, TcDecoder** out);
 void tc_decoder_destroy(TcDecoder* h);
 int tc_decoder_pack_weights(TcDecoder* h, int layer, const float* w_dev, const float* b_dev, cudaStream_t s);
 int tc_decoder_forward(TcDecoder* h, const float* z_dev, int B, float* x_out, cudaStream_t s);
+const float* tc_decoder_merged_weights(const TcDecoder* h);   // fp32 merged sub-pixel weights of the layer packed last
 
 // ---- training: backward GEMMs (tc_train.cu); units are the conv layers in backward order (decoder L..1, encoder L..2)
 struct TcTrainPlan;
@@ -44,11 +45,12 @@ float* tc_train_raw(TcTrainPlan* h);
 float* tc_train_f32_out(TcTrainPlan* h);
 int tc_train_begin_step(TcTrainPlan* h, cudaStream_t s);
 int tc_train_pack_weights(TcTrainPlan* h, int u, const float* w_dev, cudaStream_t s);
+int tc_train_pack_weights_merged(TcTrainPlan* h, int u, const float* wm_dev, cudaStream_t s);
 int tc_train_set_loss_grad(TcTrainPlan* h, const float* g_dev, int B, cudaStream_t s);
 int tc_train_set_unit_grad(TcTrainPlan* h, int u, const float* g_dev, int B, cudaStream_t s);
 int tc_train_unit_wgrad(TcTrainPlan* h, int u, int B, float* dw_out, cudaStream_t s);
 int tc_train_unit_dgrad(TcTrainPlan* h, int u, int B, cudaStream_t s);
-int tc_train_finish(TcTrainPlan* h, int u, int next, int B, bool want_f32, cudaStream_t s);
+int tc_train_finish(TcTrainPlan* h, int u, int next, int B, bool want_f32, bool keep_masked, float* db_out, cudaStream_t s);
 int tc_train_unpack_flat(TcTrainPlan* h, int B, float* out, cudaStream_t s);
 
 int tc_codebook_create(int device, const float* E_dev, int64_t n_rows, int latent, int max_batch, TcCodebook** out);

@@ -214,6 +214,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int m0 = blockIdx.x * 128;
   const int n0 = blockIdx.y * N_TILE;
   const int total_iters = p.taps * p.chunks_per_tap;
+  const int it_begin = blockIdx.z * p.iters_per_split;          // split-K (OUT_F32 partials): gridDim.z ranges of K iterations
+  const int it_end = min(total_iters, it_begin + p.iters_per_split);
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo); }
   if (warp == 1 && lane == 0) {
@@ -232,9 +234,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const int hw = p.OH * p.OW;
       const int b0 = m0 / hw, rem = m0 - b0 * hw;
       const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&empty_bar[s], (((uint32_t)(it / STAGES)) & 1u) ^ 1u);
+      for (int it = it_begin, i = 0; it < it_end; ++it, ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&empty_bar[s], (((uint32_t)(i / STAGES)) & 1u) ^ 1u);
         const int tap = it / p.chunks_per_tap, cc = it - tap * p.chunks_per_tap;
         uint8_t* st = smem + s * S::STAGE_BYTES;
         if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);   // bytes of both CTAs land on the leader's barrier
@@ -251,9 +253,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   } else if (warp == 1) {
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(256, N_TILE, 0);
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&full_bar[s], ((uint32_t)(it / STAGES)) & 1u);
+      for (int it = it_begin, i = 0; it < it_end; ++it, ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&full_bar[s], ((uint32_t)(i / STAGES)) & 1u);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
         const uint64_t a_hi = KCH == 64 ? make_sw128_kmajor_desc(st) : make_sw64_kmajor_desc(st);
@@ -262,7 +264,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const uint64_t w_lo = KCH == 64 ? make_sw128_kmajor_desc(st + 3 * S::T_BYTES) : make_sw64_kmajor_desc(st + 3 * S::T_BYTES);
 #pragma unroll
         for (int k = 0; k < KCH / 16; ++k) {
-          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+          const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
           umma_f16_2sm(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_hi, k), idesc, first);
           umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, first);
           umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
@@ -288,7 +290,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * unscale;
-      tc_store_chunk(p, row, n, f, 0);
+      tc_store_chunk(p, row, n, f, (int)blockIdx.z);
     }
   }
   tc_fence_before();
@@ -629,6 +631,48 @@ __global__ void split_scale_kernel(const float* __restrict__ x, long long n, flo
   }
 }
 
+// merged weights Wm [9][cin][n4] -> operand of the tap-separable output layer: row (tap * n4 + m) = Wm[tap][:, m], rows >= 9*n4 zero
+__global__ void pack_out_sep_kernel(const float* __restrict__ wm, int cin, int n4, float scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int total = 128 * cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % cin, n = i / cin;
+    const int tap = n / n4, m = n - tap * n4;
+    const float v = tap < 9 ? wm[((long long)tap * cin + ci) * n4 + m] * scale : 0.f;
+    __half a, d;
+    split_f16(v, a, d);
+    hi[i] = a;
+    lo[i] = d;
+  }
+}
+
+// x[b, 2i+py, 2j+px, co] = sigmoid(bias[co] + sum_{tap=(ty,tx)} P[(b, i+ty-1, j+tx-1)][tap*4c + (py*2+px)*c + co]); one thread per output value
+__global__ void outlayer_gather_kernel(const float* __restrict__ P, const float* __restrict__ bias, int B, int h, int w, int c,
+                                       float* __restrict__ x) {
+  const int n4 = 4 * c;
+  const long long total = (long long)B * h * w * n4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(t % n4);
+    long long r = t / n4;
+    const int j = (int)(r % w); r /= w;
+    const int i = (int)(r % h);
+    const long long b = r / h;
+    const int cls = m / c, co = m - cls * c;
+    float s = bias ? __ldg(bias + co) : 0.f;
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty) {
+      const int ii = i + ty - 1;
+      if (ii < 0 || ii >= h) continue;
+#pragma unroll
+      for (int tx = 0; tx < 3; ++tx) {
+        const int jj = j + tx - 1;
+        if (jj < 0 || jj >= w) continue;
+        s += P[((b * h + ii) * w + jj) * 128 + (ty * 3 + tx) * n4 + m];
+      }
+    }
+    x[((b * 2 * h + 2 * i + (cls >> 1)) * (2LL * w) + 2 * j + (cls & 1)) * c + co] = 1.f / (1.f + expf(-s));
+  }
+}
+
 __global__ void tile_bias_kernel(const float* __restrict__ b, int cout, int n_pad, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_pad) out[i] = i < 4 * cout ? b[i % cout] : 0.f;
@@ -707,7 +751,12 @@ int tc_decoder_create(int device, const aae_net_cfg* cfg, TcDecoder** out) {
       T.BW = hh; T.BH = std::min(hh, 128 / T.BW); T.BB = 128 / (T.BW * T.BH);
       g.OH = g.OW = hh;
       if (l < L) { g.N = 4 * cout; T.n_tile = 256; g.relu = 1; g.out_mode = OUT_D2S_SPLIT; }
-      else { g.N = 32; T.n_tile = 32; g.relu = 2; g.out_mode = OUT_D2S_F32; g.cout_real = cout;
+      else if (36 * cout <= 128 && T.in_c % 64 == 0 && getenv("AAE_TC_OUT9") == nullptr) {
+        h->sep_out = true;                          // 1x1 GEMM into P, neighbourhood sum in outlayer_gather_kernel
+        T.taps = 1; T.kch = 64; g.N = 128; T.n_tile = 128; g.relu = 0; g.out_mode = OUT_F32; g.cout_real = cout;
+        st = dev_alloc((void**)&h->out_p, (size_t)ceil_div((int64_t)B * hh * hh, 128) * 128 * 128 * sizeof(float));
+        if (st != AAE_OK) break;
+      } else { g.N = 32; T.n_tile = 32; g.relu = 2; g.out_mode = OUT_D2S_F32; g.cout_real = cout;
              if (4 * cout > 32) { set_error("tc decoder: output channels > 8 unsupported"); st = AAE_ERR_UNSUPPORTED; break; } }
     }
     g.BW = T.BW; g.BH = T.BH; g.taps = T.taps; g.chunks_per_tap = T.in_c / T.kch;
@@ -743,6 +792,7 @@ void tc_decoder_destroy(TcDecoder* h) {
   for (auto& T : h->layers) { cudaFree(T.in_hi); cudaFree(T.in_lo); cudaFree(T.w_hi); cudaFree(T.w_lo); }
   for (auto b : h->bias_dev) cudaFree(b);
   cudaFree(h->wm_tmp);
+  cudaFree(h->out_p);
   delete h;
 }
 
@@ -760,11 +810,20 @@ int tc_decoder_pack_weights(TcDecoder* h, int layer, const float* w_dev, const f
     if (b_dev) T.gp.bias = b_dev;      // device pointer owned by the decoder handle
     return AAE_OK;
   }
+  const bool sep = h->sep_out && layer + 1 == (int)h->layers.size();
   if (w_dev) {
     AAE_TRY(launch_merge_subpixel_weights(w_dev, T.in_c, T.out_c, h->wm_tmp, s));
-    dim3 grid((unsigned)ceil_div(4 * T.out_c, 32), (unsigned)ceil_div(T.in_c, 32), 9);
-    pack_weights_kernel<<<grid, block, 0, s>>>(h->wm_tmp, 9, T.in_c, 4 * T.out_c, W_SCALE, T.w_hi, T.w_lo);
+    if (sep) {
+      pack_out_sep_kernel<<<64, 256, 0, s>>>(h->wm_tmp, T.in_c, 4 * T.out_c, W_SCALE, T.w_hi, T.w_lo);
+    } else {
+      dim3 grid((unsigned)ceil_div(4 * T.out_c, 32), (unsigned)ceil_div(T.in_c, 32), 9);
+      pack_weights_kernel<<<grid, block, 0, s>>>(h->wm_tmp, 9, T.in_c, 4 * T.out_c, W_SCALE, T.w_hi, T.w_lo);
+    }
     AAE_LAUNCH_OK();
+  }
+  if (sep) {
+    if (b_dev) h->out_bias = b_dev;
+    return AAE_OK;
   }
   if (b_dev) {
     const int n_pad = std::max(T.gp.N, 32);
@@ -775,6 +834,8 @@ int tc_decoder_pack_weights(TcDecoder* h, int layer, const float* w_dev, const f
   return AAE_OK;
 }
 
+const float* tc_decoder_merged_weights(const TcDecoder* h) { return h->wm_tmp; }
+
 int tc_decoder_forward(TcDecoder* h, const float* z_dev, int B, float* x_out, cudaStream_t s) {
   TcLayer& D = h->layers[0];
   split_scale_kernel<<<(unsigned)std::min<int64_t>(1024, ceil_div((int64_t)B * D.in_c, 256)), 256, 0, s>>>(z_dev, (long long)B * D.in_c, ACT_SCALE,
@@ -783,9 +844,16 @@ int tc_decoder_forward(TcDecoder* h, const float* z_dev, int B, float* x_out, cu
   for (size_t i = 0; i < h->layers.size(); ++i) {
     TcLayer& T = h->layers[i];
     T.gp.M = i == 0 ? B : B * T.in_h * T.in_w;
-    if (i + 1 == h->layers.size()) T.gp.out_f32 = x_out;
+    const bool last = i + 1 == h->layers.size();
+    if (last) T.gp.out_f32 = h->sep_out ? h->out_p : x_out;
     dim3 grid((unsigned)ceil_div(T.gp.M, 128), (unsigned)ceil_div(T.gp.N, T.n_tile), 1u);
     AAE_TRY(tc_launch_layer(T, grid, s));
+    if (last && h->sep_out) {
+      const long long total = (long long)T.gp.M * 4 * T.gp.cout_real;
+      outlayer_gather_kernel<<<(unsigned)std::min<long long>(148 * 16, ceil_div(total, 256)), 256, 0, s>>>(h->out_p, h->out_bias, B, T.in_h, T.in_w,
+                                                                                                         T.gp.cout_real, x_out);
+      AAE_LAUNCH_OK();
+    }
   }
   return AAE_OK;
 }

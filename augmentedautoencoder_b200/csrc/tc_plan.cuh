@@ -88,6 +88,12 @@ struct TcDecoder {
   std::vector<TcLayer> layers;     // [0] dense_1, [1..L-1] sub-pixel convs, [L] sub-pixel output layer
   std::vector<float*> bias_dev;    // per layer: bias in GEMM-column order (dense: the caller's; convs: tiled 4x, padded)
   float* wm_tmp = nullptr;         // fp32 merged-weight scratch
+  // Output layer with 36 * Cout <= 128 (Cout = 3): "tap-separable" form.  P[pixel, (tap, cls, co)] = X[pixel, :] . Wm[tap, :, (cls, co)]
+  // is ONE 1x1 GEMM (K = Cin, N = 128) that reads the activation once instead of once per tap; the 3x3 neighbourhood sum,
+  // bias, sigmoid and depth-to-space scatter happen in a small gather kernel over P.
+  bool sep_out = false;
+  float* out_p = nullptr;          // [B*h*w (padded to 128 rows)][128] fp32
+  const float* out_bias = nullptr; // the caller's bias [Cout] (device)
   size_t wm_floats = 0;
 };
 

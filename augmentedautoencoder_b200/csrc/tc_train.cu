@@ -38,7 +38,7 @@ struct TcWgradParams {
   int chunks_per_split;    // K chunks per blockIdx.z
   int8_t tap_di[32], tap_dj[32];
   int tap_ch[32];          // channel offset of the tap's parity plane in X
-  int swap_lbo_sbo;        // bring-up switch (AAE_WG_SWAP=1): exchange the two descriptor strides
+  int m_tiles;             // taps * cin_blocks (the CTA-pair kernel pads an odd count with an idle CTA)
   TcGemmParams ep;         // epilogue: OUT_F32 partials [splits][taps*Cin][N]
 };
 
@@ -130,11 +130,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
 #pragma unroll
         for (int k = 0; k < S::KP / 16; ++k) {
           const uint32_t ko = (uint32_t)k * 16u * 128u;   // 16 pixel rows of 128 B
-          const uint32_t lbo = p.swap_lbo_sbo ? 1024u : (uint32_t)BOX_BYTES, sbo = p.swap_lbo_sbo ? (uint32_t)BOX_BYTES : 1024u;
-          const uint64_t x_hi = make_sw128_mnmajor_desc(st + ko, lbo, sbo);
-          const uint64_t x_lo = make_sw128_mnmajor_desc(st + S::X_BYTES + ko, lbo, sbo);
-          const uint64_t g_hi = make_sw128_mnmajor_desc(st + 2 * S::X_BYTES + ko, lbo, sbo);
-          const uint64_t g_lo = make_sw128_mnmajor_desc(st + 2 * S::X_BYTES + S::G_BYTES + ko, lbo, sbo);
+          const uint64_t x_hi = make_sw128_mnmajor_desc(st + ko, BOX_BYTES, 1024);
+          const uint64_t x_lo = make_sw128_mnmajor_desc(st + S::X_BYTES + ko, BOX_BYTES, 1024);
+          const uint64_t g_hi = make_sw128_mnmajor_desc(st + 2 * S::X_BYTES + ko, BOX_BYTES, 1024);
+          const uint64_t g_lo = make_sw128_mnmajor_desc(st + 2 * S::X_BYTES + S::G_BYTES + ko, BOX_BYTES, 1024);
           const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
           umma_f16(tmem_base, x_hi, g_hi, idesc, first);
           umma_f16(tmem_base + N_TILE, x_lo, g_hi, idesc, first);
@@ -170,6 +169,130 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<2 * N_TILE>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- wgrad on CTA pairs
+// Same contraction with cta_group::2: two M tiles (consecutive (tap, channel-block) pairs) share one 256-column G tile and
+// run as ONE M = 256 MMA; each CTA stages its own X tile and only HALF of the G tile (128 columns), i.e. 32 KB instead of
+// 48 KB per K chunk, which is what bounds the single-CTA kernel (shared-memory bandwidth, see tc_gemm2_kernel).
+template <int STAGES>
+struct WgSmem2 {
+  static constexpr int KP = 32;
+  static constexpr int T_BYTES = 128 * KP * 2;            // X tile and G half tile: 128 channels x KP pixels
+  static constexpr int STAGE_BYTES = 4 * T_BYTES;         // X_hi, X_lo, G_hi(half), G_lo(half)
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                 const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo, const TcWgradParams p) {
+  using S = WgSmem2<STAGES>;
+  constexpr int N_TILE = 256;
+  constexpr int BOX_BYTES = 64 * S::KP * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  // an odd number of M tiles is padded to whole pairs: the extra CTA repeats the last tile's loads and writes nothing
+  const int mt = min((int)blockIdx.x, p.m_tiles - 1);
+  const int tap = mt / p.cin_blocks, cb = mt - tap * p.cin_blocks;
+  const int m0 = blockIdx.x * 128;
+  const int n0 = blockIdx.y * N_TILE;
+  const int q_begin = blockIdx.z * p.chunks_per_split;
+  const int q_end = min(p.total_chunks, q_begin + p.chunks_per_split);
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x_hi); prefetch_tmap(&tm_x_lo); prefetch_tmap(&tm_g_hi); prefetch_tmap(&tm_g_lo); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<512>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int cols = p.OW / p.BWk;
+      const int cx = p.tap_ch[tap] + cb * 128;
+      const int di = p.tap_di[tap], dj = p.tap_dj[tap];
+      const int gn = n0 + (int)rank * 128;
+      for (int q = q_begin, i = 0; q < q_end; ++q, ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&empty_bar[s], (((uint32_t)(i / STAGES)) & 1u) ^ 1u);
+        const int b = q / p.chunks_per_image, r = q - b * p.chunks_per_image;
+        const int y0 = (r / cols) * p.BHk, x0 = (r - (r / cols) * cols) * p.BWk;
+        uint8_t* st = smem + s * S::STAGE_BYTES;
+        if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);
+        const uint32_t lb = leader_bar_addr(&full_bar[s]);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          tma_load_4d_2sm(st + g * BOX_BYTES, &tm_x_hi, lb, cx + 64 * g, x0 + dj, y0 + di, b);
+          tma_load_4d_2sm(st + S::T_BYTES + g * BOX_BYTES, &tm_x_lo, lb, cx + 64 * g, x0 + dj, y0 + di, b);
+          tma_load_4d_2sm(st + 2 * S::T_BYTES + g * BOX_BYTES, &tm_g_hi, lb, gn + 64 * g, x0, y0, b);
+          tma_load_4d_2sm(st + 3 * S::T_BYTES + g * BOX_BYTES, &tm_g_lo, lb, gn + 64 * g, x0, y0, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, N_TILE, 0) | (1u << 15) | (1u << 16);
+      for (int q = q_begin, i = 0; q < q_end; ++q, ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&full_bar[s], ((uint32_t)(i / STAGES)) & 1u);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < S::KP / 16; ++k) {
+          const uint32_t ko = (uint32_t)k * 16u * 128u;
+          const uint64_t x_hi = make_sw128_mnmajor_desc(st + ko, BOX_BYTES, 1024);
+          const uint64_t x_lo = make_sw128_mnmajor_desc(st + S::T_BYTES + ko, BOX_BYTES, 1024);
+          const uint64_t g_hi = make_sw128_mnmajor_desc(st + 2 * S::T_BYTES + ko, BOX_BYTES, 1024);
+          const uint64_t g_lo = make_sw128_mnmajor_desc(st + 3 * S::T_BYTES + ko, BOX_BYTES, 1024);
+          const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
+          umma_f16_2sm(tmem_base, x_hi, g_hi, idesc, first);
+          umma_f16_2sm(tmem_base + N_TILE, x_lo, g_hi, idesc, first);
+          umma_f16_2sm(tmem_base + N_TILE, x_hi, g_lo, idesc, 1u);
+        }
+        umma_commit_2sm(&empty_bar[s]);
+      }
+      umma_commit_2sm(tmem_full_bar);
+    }
+  } else if (warp >= 4) {
+    const int q4 = warp & 3;
+    const TcRow row = tc_decode_row(p.ep, m0 + q4 * 32 + lane);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const float unscale = p.ep.amax_bits ? p.ep.unscale * tc_dyn_unscale(__ldg(p.ep.amax_bits)) : p.ep.unscale;
+#pragma unroll 1
+    for (int c = 0; c < N_TILE / 32; ++c) {
+      uint32_t v[32], x[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
+      tmem_ld_wait();
+      const int n = n0 + c * 32;
+      if (!row.valid || n >= p.ep.N) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * unscale;
+      tc_store_chunk(p.ep, row, n, f, (int)blockIdx.z);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
   }
 }
 
@@ -239,19 +362,28 @@ __global__ void amax_kernel(const float* __restrict__ x, const __half* __restric
   }
 }
 
-// raw (fp32 dgrad result, source layout) -> ReLU mask of the forward activation (same layout as raw) -> masked fp32 back in
-// place (bias gradient / SIMT consumers) -> (hi, lo) fp16 of value * tc_dyn_scale(amax) and/or fp32, in the remapped layout
-__global__ void finish_kernel(float* __restrict__ raw, const __half* __restrict__ mask, long long groups, int mode, int h, int w, int C,
-                              const unsigned* __restrict__ amax, __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ out_f32) {
+// raw (fp32 dgrad result, source layout) -> ReLU mask of the forward activation (same layout as raw) -> (hi, lo) fp16 of
+// value * tc_dyn_scale(amax) and/or fp32 in the remapped layout; optionally the masked fp32 back in place (fp32 consumers)
+// and the per-column sums of the masked values (bias gradient): a thread always meets the same 8-column group because
+// 256 % groups_per_row == 0, so it sums in registers and the block folds the threads of a group in fixed order.
+__global__ void __launch_bounds__(256) finish_kernel(float* __restrict__ raw, const __half* __restrict__ mask, long long groups, int mode, int h, int w,
+                                                     int C, const unsigned* __restrict__ amax, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                     float* __restrict__ out_f32, int write_masked, float* __restrict__ colsum, int groups_per_row) {
+  __shared__ float red[256 * 8];
   const float scale = amax ? tc_dyn_scale(__ldg(amax)) : 1.f;
+  float cs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs[j] = 0.f;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
     const long long i = g * 8;
     float v[8];
     load8(raw + i, v);
     if (mask) {
       apply_mask8(mask + i, v);
-      store8(raw + i, v);
+      if (write_masked) store8(raw + i, v);
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] += v[j];
     const long long j = remap_offset(i, mode, h, w, C);
     if (out_f32) store8(out_f32 + j, v);
     if (hi) {
@@ -261,6 +393,41 @@ __global__ void finish_kernel(float* __restrict__ raw, const __half* __restrict_
       *reinterpret_cast<uint4*>(hi + j) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
       *reinterpret_cast<uint4*>(lo + j) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
     }
+  }
+  if (colsum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = cs[j];
+    __syncthreads();
+    if ((int)threadIdx.x < groups_per_row) {
+      for (int k = 1; k < 256 / groups_per_row; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] += red[(threadIdx.x + k * groups_per_row) * 8 + j];
+      store8(colsum + ((long long)blockIdx.x * groups_per_row + threadIdx.x) * 8, cs);
+    }
+  }
+}
+
+// db[c] = sum over blocks and over the `reps` column blocks (space-to-depth parity classes) of partial[block][rep * C + c]:
+// block = 32 columns x 32 row lanes (fixed assignment and fold order, so the result is deterministic)
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ partial, int blocks, int reps, int C, float* __restrict__ db) {
+  __shared__ float red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    const int rows = blocks * reps;
+    int r = threadIdx.y;
+    for (; r + 32 < rows; r += 64) {
+      s0 += partial[(long long)r * C + c];
+      s1 += partial[(long long)(r + 32) * C + c];
+    }
+    if (r < rows) s0 += partial[(long long)r * C + c];
+  }
+  red[threadIdx.y][threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+    for (int j = 0; j < 32; ++j) s += red[j][threadIdx.x];
+    db[c] = s;
   }
 }
 
@@ -290,6 +457,59 @@ __global__ void pack_loss_grad_kernel(const float* __restrict__ g, int B, int h,
     const long long o = ((b * h + y) * w + x) * gN + n;
     hi[o] = a;
     lo[o] = d;
+  }
+}
+
+// tap-separable output layer: G[pixel (b,y,x)][tap * n4 + m] = gs[(b, y - (ty-1), x - (tx-1))][m], gs = space-to-depth of the
+// pre-sigmoid gradient g [B, 2h, 2w, c] (m = cls * c + co); columns >= 9 * n4 stay zero.  With this im2col both the dgrad
+// (K = 128) and the wgrad (N = 128) of the layer read the big activation tensor exactly once.
+__global__ void pack_loss_grad_sep_kernel(const float* __restrict__ g, int B, int h, int w, int c, const unsigned* __restrict__ amax,
+                                          __half* __restrict__ hi, __half* __restrict__ lo) {
+  const float scale = tc_dyn_scale(__ldg(amax));
+  const int n4 = 4 * c;
+  const long long total = (long long)B * h * w * 9;       // one thread per (pixel, tap): n4 consecutive columns
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 9);
+    long long r = i / 9;
+    const int x = (int)(r % w); r /= w;
+    const int y = (int)(r % h);
+    const long long b = r / h;
+    const int ys = y - (tap / 3 - 1), xs = x - (tap % 3 - 1);
+    const bool in = ys >= 0 && ys < h && xs >= 0 && xs < w;
+    const long long o = ((b * h + y) * w + x) * 128 + tap * n4;
+    for (int cls = 0; cls < 4; ++cls) {
+      const float* src = g + ((b * 2 * h + 2 * ys + (cls >> 1)) * (2LL * w) + 2 * xs + (cls & 1)) * c;
+      for (int co = 0; co < c; ++co) {
+        __half a, d;
+        split_f16(in ? src[co] * scale : 0.f, a, d);
+        hi[o + cls * c + co] = a;
+        lo[o + cls * c + co] = d;
+      }
+    }
+  }
+}
+
+// tap-separable output layer: dgrad operand [cin][128], column (tap * n4 + m) = Wm[tap][ci][m]
+__global__ void pack_dec_dgrad_sep_kernel(const float* __restrict__ wm, int cin, int n4, float scale, __half* __restrict__ hi,
+                                          __half* __restrict__ lo) {
+  const int total = cin * 128;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i & 127, ci = i >> 7;
+    const int tap = k / n4, m = k - tap * n4;
+    const float v = tap < 9 ? wm[((long long)tap * cin + ci) * n4 + m] * scale : 0.f;
+    __half a, d;
+    split_f16(v, a, d);
+    hi[i] = a;
+    lo[i] = d;
+  }
+}
+
+// wgrad result of the tap-separable layer [cin][128] (column = tap * n4 + m) -> merged-gradient layout [9][cin][n4]
+__global__ void rearrange_sep_wgrad_kernel(const float* __restrict__ in, int cin, int n4, float* __restrict__ out) {
+  const int total = 9 * cin * n4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int m = i % n4, ci = (i / n4) % cin, tap = i / (n4 * cin);
+    out[i] = in[ci * 128 + tap * n4 + m];
   }
 }
 
@@ -358,6 +578,18 @@ int launch_wgrad(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap
   return AAE_OK;
 }
 
+template <int STAGES>
+int launch_wgrad2(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& gh, const CUtensorMap& gl, const TcWgradParams& p, dim3 grid,
+                  cudaStream_t s) {
+  using S = WgSmem2<STAGES>;
+  auto kern = tc_wgrad2_kernel<STAGES>;
+  AAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  grid.x = (grid.x + 1) & ~1u;
+  kern<<<grid, 256, S::TOTAL, s>>>(xh, xl, gh, gl, p);
+  AAE_LAUNCH_OK();
+  return AAE_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------- plan
@@ -366,7 +598,9 @@ struct TcUnit {
   int cin, cout;            // the layer's real channel counts
   int gh, gw, gN;           // G = pre-activation gradient of the layer's GEMM output: plain [B, gh, gw, gN]
   int n_real;               // real columns of G (4*cout for the decoder output layer whose gN is padded)
-  int taps_w;               // taps of the wgrad (25 / 9)
+  int taps_w;               // taps of the wgrad (25 / 9; 1 for the tap-separable output layer)
+  int dg_taps;              // taps of the dgrad conv over G (9; 1 for the tap-separable output layer)
+  bool sep;                 // decoder output layer in tap-separable form: G is the im2col [pixel][(tap, cls, co)] of the loss gradient
   TcLayer dg;               // dgrad GEMM: A = G (dg.in_hi / in_lo are the G buffers), B = re-packed weights
   int nd;                   // dgrad output columns (decoder: cin, encoder: 4*cin)
   const __half *x_hi, *x_lo;  // the layer's forward input (owned by the encoder / decoder plan)
@@ -418,7 +652,7 @@ static int make_wgrad_maps(TcUnit& U, int x_c_total, int x_bpad, int g_bpad) {
   w.ep.N = U.gN;
   w.ep.OH = w.ep.OW = 1;
   w.ep.unscale = 1.f / ACT_SCALE;
-  w.swap_lbo_sbo = getenv("AAE_WG_SWAP") != nullptr ? 1 : 0;
+  w.m_tiles = U.taps_w * w.cin_blocks;
   U.wg_n_tile = U.gN >= 256 ? 256 : 64;
   return AAE_OK;
 }
@@ -438,7 +672,7 @@ int tc_train_create(TcEncoder* enc, TcDecoder* dec, int max_batch, TcTrainPlan**
     memset(&T.gp, 0, sizeof(T.gp));
     T.in_h = U.gh; T.in_w = U.gw; T.in_c = U.gN;
     T.out_h = U.gh; T.out_w = U.gw; T.out_c = U.nd;
-    T.taps = 9;
+    T.taps = U.dg_taps;
     T.BW = U.gw; T.BH = std::min(U.gh, 128 / T.BW); T.BB = 128 / (T.BW * T.BH);
     T.n_tile = U.nd >= 256 ? 256 : 128;
     T.kch = T.n_tile == 256 ? 32 : 64;
@@ -449,8 +683,12 @@ int tc_train_create(TcEncoder* enc, TcDecoder* dec, int max_batch, TcTrainPlan**
     }
     TcGemmParams& g = T.gp;
     g.N = U.nd; g.OH = U.gh; g.OW = U.gw; g.BW = T.BW; g.BH = T.BH;
-    g.taps = 9; g.chunks_per_tap = U.gN / T.kch; g.iters_per_split = g.taps * g.chunks_per_tap;
-    for (int t = 0; t < 9; ++t) { g.tap_di[t] = (int8_t)(t / 3 - 1); g.tap_dj[t] = (int8_t)(t % 3 - 1); g.tap_ch[t] = 0; }
+    g.taps = T.taps; g.chunks_per_tap = U.gN / T.kch; g.iters_per_split = g.taps * g.chunks_per_tap;
+    for (int t = 0; t < T.taps; ++t) {
+      g.tap_di[t] = (int8_t)(T.taps == 1 ? 0 : t / 3 - 1);
+      g.tap_dj[t] = (int8_t)(T.taps == 1 ? 0 : t % 3 - 1);
+      g.tap_ch[t] = 0;
+    }
     g.unscale = 1.f / W_SCALE;
     g.out_mode = OUT_F32;
     AAE_TRY(tc_layer_setup_plain(T, B, /*pair_ok=*/true, /*alloc_input=*/true));
@@ -467,11 +705,12 @@ int tc_train_create(TcEncoder* enc, TcDecoder* dec, int max_batch, TcTrainPlan**
     TcUnit U;
     U.enc = false; U.cin = F.in_c; U.cout = F.out_c;
     U.gh = F.in_h; U.gw = F.in_w;
-    U.n_real = 4 * F.out_c;
-    U.gN = l == Ld ? 64 : 4 * F.out_c;
-    U.taps_w = 9; U.nd = F.in_c;
+    U.sep = l == Ld && dec->sep_out;
+    U.n_real = U.sep ? 36 * F.out_c : 4 * F.out_c;
+    U.gN = U.sep ? 128 : (l == Ld ? 64 : 4 * F.out_c);
+    U.taps_w = U.sep ? 1 : 9; U.dg_taps = U.sep ? 1 : 9; U.nd = F.in_c;
     U.mask_hi = F.in_hi;                                   // dgrad result = gradient wrt this layer's input activation
-    if (l == Ld && U.n_real > 64) { set_error("tensor-core trainer: output channels > 16 unsupported"); st = AAE_ERR_UNSUPPORTED; break; }
+    if (l == Ld && U.n_real > U.gN) { set_error("tensor-core trainer: output channels > 16 unsupported"); st = AAE_ERR_UNSUPPORTED; break; }
     h->units.push_back(U);
     st = add_unit(h->units.back(), F, F.in_c);
   }
@@ -481,7 +720,7 @@ int tc_train_create(TcEncoder* enc, TcDecoder* dec, int max_batch, TcTrainPlan**
     TcUnit U;
     U.enc = true; U.cin = F.in_c; U.cout = F.out_c;
     U.gh = F.out_h; U.gw = F.out_w; U.gN = F.out_c; U.n_real = F.out_c;
-    U.taps_w = 25; U.nd = 4 * F.in_c;
+    U.taps_w = 25; U.dg_taps = 9; U.sep = false; U.nd = 4 * F.in_c;
     U.mask_hi = F.in_hi;                                   // space-to-depth activation, same layout as the dgrad result
     h->units.push_back(U);
     st = add_unit(h->units.back(), F, 4 * F.in_c);
@@ -525,7 +764,15 @@ int tc_train_pack_weights(TcTrainPlan* h, int u, const float* w_dev, cudaStream_
     return AAE_OK;
   }
   AAE_TRY(launch_merge_subpixel_weights(w_dev, U.cin, U.cout, h->wm, s));
-  pack_dec_dgrad_kernel<<<ew_grid((long long)U.cin * 9 * U.gN), 256, 0, s>>>(h->wm, U.cin, U.n_real, U.gN, W_SCALE, U.dg.w_hi, U.dg.w_lo);
+  return tc_train_pack_weights_merged(h, u, h->wm, s);
+}
+
+// decoder unit: dgrad operand from the already merged sub-pixel weights Wm [9][cin][4*cout] (device pointer)
+int tc_train_pack_weights_merged(TcTrainPlan* h, int u, const float* wm_dev, cudaStream_t s) {
+  AAE_REQUIRE(u >= 0 && u < h->n_dec, "tc trainer: unit %d is not a decoder unit", u);
+  TcUnit& U = h->units[u];
+  if (U.sep) pack_dec_dgrad_sep_kernel<<<ew_grid((long long)U.cin * 128), 256, 0, s>>>(wm_dev, U.cin, 4 * U.cout, W_SCALE, U.dg.w_hi, U.dg.w_lo);
+  else pack_dec_dgrad_kernel<<<ew_grid((long long)U.cin * 9 * U.gN), 256, 0, s>>>(wm_dev, U.cin, U.n_real, U.gN, W_SCALE, U.dg.w_hi, U.dg.w_lo);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }
@@ -537,7 +784,8 @@ int tc_train_set_loss_grad(TcTrainPlan* h, const float* g_dev, int B, cudaStream
   const long long n = (long long)B * U.gh * U.gw * 4 * c;
   amax_scalar_kernel<<<ew_grid(n), 256, 0, s>>>(g_dev, n, h->amax + 0);
   AAE_LAUNCH_OK();
-  pack_loss_grad_kernel<<<ew_grid(n), 256, 0, s>>>(g_dev, B, U.gh, U.gw, c, U.gN, h->amax + 0, U.dg.in_hi, U.dg.in_lo);
+  if (U.sep) pack_loss_grad_sep_kernel<<<ew_grid((long long)B * U.gh * U.gw * 9), 256, 0, s>>>(g_dev, B, U.gh, U.gw, c, h->amax + 0, U.dg.in_hi, U.dg.in_lo);
+  else pack_loss_grad_kernel<<<ew_grid(n), 256, 0, s>>>(g_dev, B, U.gh, U.gw, c, U.gN, h->amax + 0, U.dg.in_hi, U.dg.in_lo);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }
@@ -549,7 +797,7 @@ int tc_train_set_unit_grad(TcTrainPlan* h, int u, const float* g_dev, int B, cud
   amax_kernel<<<ew_grid(groups), 256, 0, s>>>(g_dev, nullptr, groups, h->amax + u);
   AAE_LAUNCH_OK();
   finish_kernel<<<ew_grid(groups), 256, 0, s>>>(const_cast<float*>(g_dev), nullptr, groups, REMAP_SAME, U.gh, U.gw, U.gN, h->amax + u, U.dg.in_hi,
-                                                U.dg.in_lo, nullptr);
+                                                U.dg.in_lo, nullptr, 0, nullptr, 1);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }
@@ -570,11 +818,17 @@ int tc_train_unit_wgrad(TcTrainPlan* h, int u, int B, float* dw_out, cudaStream_
   w.ep.amax_bits = h->amax + u;
   w.ep.out_f32 = h->partials;
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
-  if (U.wg_n_tile == 256) AAE_TRY((launch_wgrad<256, 4>(U.tm_x_hi, U.tm_x_lo, U.tm_g_hi, U.tm_g_lo, w, grid, s)));
+  if (U.wg_n_tile == 256 && getenv("AAE_WG_1CTA") == nullptr) AAE_TRY((launch_wgrad2<6>(U.tm_x_hi, U.tm_x_lo, U.tm_g_hi, U.tm_g_lo, w, grid, s)));
+  else if (U.wg_n_tile == 256) AAE_TRY((launch_wgrad<256, 4>(U.tm_x_hi, U.tm_x_lo, U.tm_g_hi, U.tm_g_lo, w, grid, s)));
   else AAE_TRY((launch_wgrad<64, 6>(U.tm_x_hi, U.tm_x_lo, U.tm_g_hi, U.tm_g_lo, w, grid, s)));
   if (U.gN == U.n_real) return launch_splitk_reduce(h->partials, splits, mn, w.ep.N, nullptr, ACT_NONE, dw_out, s);
   AAE_REQUIRE((size_t)mn <= h->wm_floats, "tc trainer: merged-gradient scratch too small");
   AAE_TRY(launch_splitk_reduce(h->partials, splits, mn, w.ep.N, nullptr, ACT_NONE, h->wm, s));
+  if (U.sep) {
+    rearrange_sep_wgrad_kernel<<<ew_grid(9LL * U.cin * 4 * U.cout), 256, 0, s>>>(h->wm, U.cin, 4 * U.cout, dw_out);
+    AAE_LAUNCH_OK();
+    return AAE_OK;
+  }
   compact_cols_kernel<<<ew_grid((long long)w.ep.M * U.n_real), 256, 0, s>>>(h->wm, w.ep.M, U.gN, U.n_real, dw_out);
   AAE_LAUNCH_OK();
   return AAE_OK;
@@ -586,14 +840,26 @@ int tc_train_unit_dgrad(TcTrainPlan* h, int u, int B, cudaStream_t s) {
   TcLayer& T = U.dg;
   T.gp.M = B * U.gh * U.gw;
   T.gp.amax_bits = h->amax + u;
-  T.gp.out_f32 = h->raw;
-  dim3 grid((unsigned)ceil_div(T.gp.M, 128), (unsigned)(U.nd / T.n_tile), 1u);
-  return tc_launch_layer(T, grid, s);
+  const int m_tiles = (int)ceil_div(T.gp.M, 128), n_tiles = U.nd / T.n_tile;
+  const int total_iters = T.gp.taps * T.gp.chunks_per_tap;
+  // few output tiles and a long K (the 8x8 layers): split K so that the grid covers the SMs, fold the partials afterwards
+  int splits = std::max(1, 148 / std::max(1, ((m_tiles + 1) & ~1) * n_tiles));
+  splits = std::min(splits, std::max(1, total_iters / 64));
+  const long long mn = (long long)T.gp.M * U.nd;
+  if ((size_t)splits * (size_t)mn > h->partial_floats) splits = 1;
+  T.gp.iters_per_split = (int)ceil_div(total_iters, splits);
+  splits = (int)ceil_div(total_iters, T.gp.iters_per_split);
+  T.gp.out_f32 = splits > 1 ? h->partials : h->raw;
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+  AAE_TRY(tc_launch_layer(T, grid, s));
+  if (splits > 1) AAE_TRY(launch_splitk_reduce(h->partials, splits, mn, U.nd, nullptr, ACT_NONE, h->raw, s));
+  return AAE_OK;
 }
 
-// raw of unit u -> masked in place; when next >= 0 also re-split into G of unit `next`; when f32_out also written as fp32 in
-// the remapped layout.  Layout change: decoder plain -> space-to-depth (the producing layer's GEMM columns), encoder the reverse.
-int tc_train_finish(TcTrainPlan* h, int u, int next, int B, bool want_f32, cudaStream_t s) {
+// raw of unit u -> ReLU mask -> G of unit `next` (when next >= 0) and/or fp32 in the remapped layout (want_f32), the masked
+// fp32 back in place (keep_masked) and its per-channel sums db_out (bias gradient of the layer that produced the masked
+// activation).  Layout change: decoder plain -> space-to-depth (the producing layer's GEMM columns), encoder the reverse.
+int tc_train_finish(TcTrainPlan* h, int u, int next, int B, bool want_f32, bool keep_masked, float* db_out, cudaStream_t s) {
   TcUnit& U = h->units[u];
   const long long groups = (long long)B * U.gh * U.gw * U.nd / 8;
   __half *hi = nullptr, *lo = nullptr;
@@ -608,8 +874,21 @@ int tc_train_finish(TcTrainPlan* h, int u, int next, int B, bool want_f32, cudaS
   const int mode = U.enc ? REMAP_S2D_TO_PLAIN : (next >= 0 ? REMAP_PLAIN_TO_S2D : REMAP_SAME);
   // source dims: decoder raw is plain [B, gh, gw, nd]; encoder raw is [B, gh, gw, (cls, cin)]
   const int C = U.enc ? U.cin : U.nd;
-  finish_kernel<<<ew_grid(groups), 256, 0, s>>>(h->raw, U.mask_hi, groups, mode, U.gh, U.gw, C, slot, hi, lo, want_f32 ? h->f32_out : nullptr);
+  const int gpr = U.nd / 8;                          // 8-column groups per raw row
+  const unsigned grid = ew_grid(groups);
+  float* colsum = nullptr;
+  if (db_out) {
+    AAE_REQUIRE(gpr <= 256 && 256 % gpr == 0, "tc trainer: %d columns unsupported by the fused bias gradient", U.nd);
+    AAE_REQUIRE((size_t)grid * U.nd <= h->partial_floats, "tc trainer: column-sum scratch too small");
+    colsum = h->partials;
+  }
+  finish_kernel<<<grid, 256, 0, s>>>(h->raw, U.mask_hi, groups, mode, U.gh, U.gw, C, slot, hi, lo, want_f32 ? h->f32_out : nullptr,
+                                     keep_masked ? 1 : 0, colsum, std::max(gpr, 1));
   AAE_LAUNCH_OK();
+  if (db_out) {
+    colsum_final_kernel<<<(unsigned)ceil_div(C, 32), dim3(32, 32), 0, s>>>(colsum, (int)grid, U.nd / C, C, db_out);
+    AAE_LAUNCH_OK();
+  }
   return AAE_OK;
 }
 
