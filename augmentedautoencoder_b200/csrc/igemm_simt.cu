@@ -325,6 +325,22 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partials, int spl
   out[i] = s;
 }
 
+// float4 variant for MN % 4 == 0, N % 4 == 0 (every large caller): 4x fewer threads, 16-byte accesses
+__global__ void splitk_reduce4_kernel(const float4* __restrict__ partials, int splits, long long MN4, int N4, const float4* __restrict__ bias,
+                                      int act, float4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MN4) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < splits; ++z) {
+    const float4 v = partials[(long long)z * MN4 + i];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  if (bias) { const float4 b = bias[i % N4]; s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w; }
+  if (act == ACT_RELU) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+  else if (act == ACT_SIGMOID) { s.x = 1.f / (1.f + expf(-s.x)); s.y = 1.f / (1.f + expf(-s.y)); s.z = 1.f / (1.f + expf(-s.z)); s.w = 1.f / (1.f + expf(-s.w)); }
+  out[i] = s;
+}
+
 template <int MODE>
 int launch_mode(const IGemmParams& p, dim3 grid, cudaStream_t stream, bool vec) {
   if (p.src_u8) {
@@ -366,7 +382,13 @@ int launch_igemm(const IGemmParams& p, int mode, cudaStream_t stream) {
 int launch_splitk_reduce(const float* partials, int splits, int64_t MN, int N, const float* bias, int act, float* out,
                          cudaStream_t stream) {
   const int threads = 256;
-  splitk_reduce_kernel<<<(unsigned)ceil_div(MN, threads), threads, 0, stream>>>(partials, splits, MN, N, bias, act, out);
+  const bool aligned = ((uintptr_t)partials % 16 == 0) && ((uintptr_t)out % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0);
+  if (MN % 4 == 0 && N % 4 == 0 && aligned && MN >= (1 << 20))   // small outputs: keep one thread per element for parallelism
+    splitk_reduce4_kernel<<<(unsigned)ceil_div(MN / 4, threads), threads, 0, stream>>>(reinterpret_cast<const float4*>(partials), splits, MN / 4, N / 4,
+                                                                                     reinterpret_cast<const float4*>(bias), act,
+                                                                                     reinterpret_cast<float4*>(out));
+  else
+    splitk_reduce_kernel<<<(unsigned)ceil_div(MN, threads), threads, 0, stream>>>(partials, splits, MN, N, bias, act, out);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }

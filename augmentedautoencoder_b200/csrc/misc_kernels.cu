@@ -171,9 +171,9 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamBatch b, floa
 // Weight gradient of the first encoder layer (5x5, stride 2, Cin = 3, Cout = 128; auto_pose/ae/encoder.py:43-50):
 //   dW[(kh,kw,ci), co] = sum_pixels X[2*oy + kh - pad, 2*ox + kw - pad, ci] * dY[oy, ox, co]      (75 x 128 outputs, K = B*OH*OW)
 // A 75-row GEMM wastes a 128-row tile of the generic implicit GEMM and its gather is 75 scattered loads per pixel; here a
-// CTA stages the input rows of 4 output rows once (zero-padded patch), streams dY through a cp.async double buffer and every
+// CTA stages the input rows of 2 output rows once (zero-padded patch), streams dY through a cp.async double buffer and every
 // thread keeps a 5 (k) x 8 (co) register block.  Persistent CTAs write partial sums [CTA][75*128], folded by splitk_reduce.
-constexpr int C1W_RB = 4, C1W_CH = 64, C1W_N = 128, C1W_K = 75;
+constexpr int C1W_RB = 2, C1W_CH = 64, C1W_N = 128, C1W_K = 75;
 __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int H, int W, int OH,
                                                           int OW, int pad_t, int pad_l, float* __restrict__ partial) {
   extern __shared__ float c1w_smem[];

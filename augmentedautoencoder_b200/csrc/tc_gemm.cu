@@ -15,7 +15,7 @@
 // buffer, no stride-2 gathers.  Weights are pre-packed [Cout][25*Cin] K-major.  Both operands land in shared memory in
 // the 128-byte-swizzle canonical layout tcgen05.mma consumes directly.
 //
-// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue, two per TMEM lane quadrant
 // (TMEM -> registers -> bias/ReLU -> hi/lo split -> global, in the next layer's space-to-depth layout).
 #include <stdlib.h>
 
@@ -68,7 +68,7 @@ struct TcSmem {
 };
 
 template <int N_TILE, int STAGES, int KCH>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const TcGemmParams p) {
   using S = TcSmem<N_TILE, STAGES, KCH>;
@@ -152,14 +152,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - 4) >> 2;   // two warps per TMEM lane quadrant, interleaved 32-column chunks
+    const int epi_groups = ((int)blockDim.x >> 5) > 8 ? 2 : 1;
     const TcRow row = tc_decode_row(p, m0 + q * 32 + lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const bool has_work = it_end > it_begin;
     const float unscale = p.amax_bits ? p.unscale * tc_dyn_unscale(__ldg(p.amax_bits)) : p.unscale;
 #pragma unroll 1
-    for (int c = 0; c < N_TILE / 32; ++c) {
+    for (int c = half; c < N_TILE / 32; c += epi_groups) {
       uint32_t v[32], x[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
@@ -196,7 +197,7 @@ struct TcSmem2 {
 };
 
 template <int STAGES, int KCH>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const TcGemmParams p) {
   using S = TcSmem2<STAGES, KCH>;
@@ -274,13 +275,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       umma_commit_2sm(tmem_full_bar);
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - 4) >> 2;   // two warps per TMEM lane quadrant, interleaved 32-column chunks
+    const int epi_groups = ((int)blockDim.x >> 5) > 8 ? 2 : 1;
     const TcRow row = tc_decode_row(p, m0 + q * 32 + lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const float unscale = p.amax_bits ? p.unscale * tc_dyn_unscale(__ldg(p.amax_bits)) : p.unscale;
 #pragma unroll 1
-    for (int c = 0; c < N_TILE / 32; ++c) {
+    for (int c = half; c < N_TILE / 32; c += epi_groups) {
       uint32_t v[32], x[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
@@ -354,7 +356,7 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
   auto kern = tc_gemm2_kernel<STAGES, KCH>;
   AAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   grid.x = (grid.x + 1) & ~1u;   // whole CTA pairs
-  kern<<<grid, 256, S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w2_hi, L.tm_w2_lo, L.gp);
+  kern<<<grid, tc_block_threads(), S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w2_hi, L.tm_w2_lo, L.gp);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }
@@ -364,7 +366,7 @@ int launch_tc_gemm(const TcLayer& L, dim3 grid, cudaStream_t s) {
   using S = TcSmem<N_TILE, STAGES, KCH>;
   auto kern = tc_gemm_kernel<N_TILE, STAGES, KCH>;
   AAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-  kern<<<grid, 256, S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w_hi, L.tm_w_lo, L.gp);
+  kern<<<grid, tc_block_threads(), S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w_hi, L.tm_w_lo, L.gp);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }

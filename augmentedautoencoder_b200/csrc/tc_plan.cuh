@@ -1,6 +1,8 @@
 // Execution-plan structures of the tensor-core path, shared by tc_gemm.cu (inference plans, GEMM kernels) and
 // tc_train.cu (backward plans).  Internal to the library.
 #pragma once
+#include <stdlib.h>
+
 #include <vector>
 
 #include "tc.cuh"
@@ -52,6 +54,12 @@ __device__ __forceinline__ float tc_dyn_unscale(unsigned amax_bits) { return __i
 constexpr float ACT_SCALE = 16.f;     // activations (and the [0,1] input) are stored as 16 * x
 constexpr float W_SCALE = 256.f;      // weights are stored as 256 * w
 constexpr int TC_STAGES = 2;
+constexpr int TC_THREADS = 384;       // warp 0 TMA, 1 MMA, 2 TMEM allocator, 3 idle, 4-11 epilogue (two per TMEM lane quadrant)
+// AAE_TC_EPI4=1 launches 256 threads (one epilogue warp per quadrant) for A/B measurements
+inline int tc_block_threads() {
+  static const int n = getenv("AAE_TC_EPI4") ? 256 : TC_THREADS;
+  return n;
+}
 
 struct TcLayer {
   int in_h, in_w, in_c, out_h, out_w, out_c;   // conv geometry (input is the space-to-depth tensor [B, in_h/2, in_w/2, 4*in_c])

@@ -64,7 +64,7 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, 
 }
 
 template <int N_TILE, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                 const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo, const TcWgradParams p) {
   using S = WgSmem<N_TILE, STAGES>;
@@ -144,14 +144,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
       umma_commit(tmem_full_bar);
     }
   } else if (warp >= 4) {
-    const int q4 = warp & 3;
+    const int q4 = warp & 3, half = (warp - 4) >> 2;
+    const int epi_groups = ((int)blockDim.x >> 5) > 8 ? 2 : 1;
     const TcRow row = tc_decode_row(p.ep, m0 + q4 * 32 + lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const bool has_work = q_end > q_begin;
     const float unscale = p.ep.amax_bits ? p.ep.unscale * tc_dyn_unscale(__ldg(p.ep.amax_bits)) : p.ep.unscale;
 #pragma unroll 1
-    for (int c = 0; c < N_TILE / 32; ++c) {
+    for (int c = half; c < N_TILE / 32; c += epi_groups) {
       uint32_t v[32], x[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 32), v);
       tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
@@ -185,7 +186,7 @@ struct WgSmem2 {
 };
 
 template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                  const __grid_constant__ CUtensorMap tm_g_hi, const __grid_constant__ CUtensorMap tm_g_lo, const TcWgradParams p) {
   using S = WgSmem2<STAGES>;
@@ -269,13 +270,14 @@ tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       umma_commit_2sm(tmem_full_bar);
     }
   } else if (warp >= 4) {
-    const int q4 = warp & 3;
+    const int q4 = warp & 3, half = (warp - 4) >> 2;
+    const int epi_groups = ((int)blockDim.x >> 5) > 8 ? 2 : 1;
     const TcRow row = tc_decode_row(p.ep, m0 + q4 * 32 + lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const float unscale = p.ep.amax_bits ? p.ep.unscale * tc_dyn_unscale(__ldg(p.ep.amax_bits)) : p.ep.unscale;
 #pragma unroll 1
-    for (int c = 0; c < N_TILE / 32; ++c) {
+    for (int c = half; c < N_TILE / 32; c += epi_groups) {
       uint32_t v[32], x[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 32), v);
       tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
@@ -415,12 +417,16 @@ __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restr
   float s0 = 0.f, s1 = 0.f;
   if (c < C) {
     const int rows = blocks * reps;
+    float s2 = 0.f, s3 = 0.f;
     int r = threadIdx.y;
-    for (; r + 32 < rows; r += 64) {
+    for (; r + 96 < rows; r += 128) {
       s0 += partial[(long long)r * C + c];
       s1 += partial[(long long)(r + 32) * C + c];
+      s2 += partial[(long long)(r + 64) * C + c];
+      s3 += partial[(long long)(r + 96) * C + c];
     }
-    if (r < rows) s0 += partial[(long long)r * C + c];
+    for (; r < rows; r += 32) s0 += partial[(long long)r * C + c];
+    s0 += s2; s1 += s3;
   }
   red[threadIdx.y][threadIdx.x] = s0 + s1;
   __syncthreads();
@@ -477,14 +483,19 @@ __global__ void pack_loss_grad_sep_kernel(const float* __restrict__ g, int B, in
     const int ys = y - (tap / 3 - 1), xs = x - (tap % 3 - 1);
     const bool in = ys >= 0 && ys < h && xs >= 0 && xs < w;
     const long long o = ((b * h + y) * w + x) * 128 + tap * n4;
-    for (int cls = 0; cls < 4; ++cls) {
-      const float* src = g + ((b * 2 * h + 2 * ys + (cls >> 1)) * (2LL * w) + 2 * xs + (cls & 1)) * c;
-      for (int co = 0; co < c; ++co) {
-        __half a, d;
-        split_f16(in ? src[co] * scale : 0.f, a, d);
-        hi[o + cls * c + co] = a;
-        lo[o + cls * c + co] = d;
+    // n4 = 4c values -> c groups of 4 halves (8 bytes) each for hi and lo
+    for (int q = 0; q < c; ++q) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int m = q * 4 + e, cls = m / c, co = m - cls * c;
+        v[e] = in ? g[((b * 2 * h + 2 * ys + (cls >> 1)) * (2LL * w) + 2 * xs + (cls & 1)) * c + co] * scale : 0.f;
       }
+      uint32_t h0, l0, h1, l1;
+      split_f16x2(v[0], v[1], h0, l0);
+      split_f16x2(v[2], v[3], h1, l1);
+      *reinterpret_cast<uint2*>(hi + o + q * 4) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(lo + o + q * 4) = make_uint2(l0, l1);
     }
   }
 }
@@ -573,7 +584,7 @@ int launch_wgrad(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap
   using S = WgSmem<N_TILE, STAGES>;
   auto kern = tc_wgrad_kernel<N_TILE, STAGES>;
   AAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-  kern<<<grid, 256, S::TOTAL, s>>>(xh, xl, gh, gl, p);
+  kern<<<grid, tc_block_threads(), S::TOTAL, s>>>(xh, xl, gh, gl, p);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }
@@ -585,7 +596,7 @@ int launch_wgrad2(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMa
   auto kern = tc_wgrad2_kernel<STAGES>;
   AAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   grid.x = (grid.x + 1) & ~1u;
-  kern<<<grid, 256, S::TOTAL, s>>>(xh, xl, gh, gl, p);
+  kern<<<grid, tc_block_threads(), S::TOTAL, s>>>(xh, xl, gh, gl, p);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }
@@ -875,7 +886,8 @@ int tc_train_finish(TcTrainPlan* h, int u, int next, int B, bool want_f32, bool 
   // source dims: decoder raw is plain [B, gh, gw, nd]; encoder raw is [B, gh, gw, (cls, cin)]
   const int C = U.enc ? U.cin : U.nd;
   const int gpr = U.nd / 8;                          // 8-column groups per raw row
-  const unsigned grid = ew_grid(groups);
+  // with the fused column sums every block leaves one partial row: 4 blocks per SM keep the fold short
+  const unsigned grid = db_out ? std::min(ew_grid(groups), 148u * 4u) : ew_grid(groups);
   float* colsum = nullptr;
   if (db_out) {
     AAE_REQUIRE(gpr <= 256 && 256 % gpr == 0, "tc trainer: %d columns unsupported by the fused bias gradient", U.nd);
