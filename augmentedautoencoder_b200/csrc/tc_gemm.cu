@@ -303,6 +303,153 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------- persistent 2-CTA kernel
+// One CTA pair per SM pair walks over the output tiles (m pair fastest, so that concurrently running pairs share the weight
+// tile in L2).  Barrier setup, TMEM allocation and the launch of a fresh CTA are paid once, and the TMA producer runs ahead
+// through the shared-memory ring while the epilogue of the previous tile drains TMEM, so the next tile's MMAs start on full
+// stages: per tile only the epilogue itself is exposed (the accumulators occupy all 512 TMEM columns, so it is not
+// double-buffered).  tmem_empty (leader CTA) collects one arrival per epilogue warp of BOTH CTAs before the issuer
+// overwrites the accumulators.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+struct TcTileSched {
+  int m_pairs, n_tiles, splits;   // tiles = m_pairs * n_tiles * splits, each tile = 256 rows x 256 columns x one K range
+};
+
+template <int STAGES, int KCH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const TcGemmParams p,
+                 const TcTileSched sch) {
+  using S = TcSmem2<STAGES, KCH>;
+  constexpr int N_TILE = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_epi_warps = ((int)blockDim.x >> 5) - 4;
+  const int total_iters = p.taps * p.chunks_per_tap;
+  const int n_tiles_total = sch.m_pairs * sch.n_tiles * sch.splits;
+  const int first_tile = (int)(blockIdx.x >> 1), tile_step = (int)(gridDim.x >> 1);
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(tmem_empty_bar, 2 * n_epi_warps);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<512>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int hw = p.OH * p.OW;
+      int g = 0;                                               // ring position, continues across tiles
+      for (int t = first_tile; t < n_tiles_total; t += tile_step) {
+        const int mp = t % sch.m_pairs, r = t / sch.m_pairs, ny = r % sch.n_tiles, z = r / sch.n_tiles;
+        const int m0 = (mp * 2 + (int)rank) * 128, n0 = ny * N_TILE;
+        const int b0 = m0 / hw, rem = m0 - b0 * hw;
+        const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
+        const int it_begin = z * p.iters_per_split, it_end = min(total_iters, it_begin + p.iters_per_split);
+        for (int it = it_begin; it < it_end; ++it, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&empty_bar[s], (((uint32_t)(g / STAGES)) & 1u) ^ 1u);
+          const int tap = it / p.chunks_per_tap, cc = it - tap * p.chunks_per_tap;
+          uint8_t* st = smem + s * S::STAGE_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);
+          const uint32_t lb = leader_bar_addr(&full_bar[s]);
+          const int c0 = p.tap_ch[tap] + cc * KCH;
+          const int x = ow0 + p.tap_dj[tap], y = oh0 + p.tap_di[tap];
+          tma_load_4d_2sm(st, &tm_a_hi, lb, c0, x, y, b0);
+          tma_load_4d_2sm(st + S::T_BYTES, &tm_a_lo, lb, c0, x, y, b0);
+          const int kcol = it * KCH;
+          tma_load_2d_2sm(st + 2 * S::T_BYTES, &tm_w_hi, lb, kcol, n0 + (int)rank * 128);
+          tma_load_2d_2sm(st + 3 * S::T_BYTES, &tm_w_lo, lb, kcol, n0 + (int)rank * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, N_TILE, 0);
+      int g = 0, tl = 0;
+      for (int t = first_tile; t < n_tiles_total; t += tile_step, ++tl) {
+        const int z = (t / sch.m_pairs) / sch.n_tiles;
+        const int it_begin = z * p.iters_per_split, it_end = min(total_iters, it_begin + p.iters_per_split);
+        if (tl > 0) {                                           // both CTAs' epilogues have drained the previous accumulators
+          mbar_wait(tmem_empty_bar, (uint32_t)(tl - 1) & 1u);
+          tc_fence_after();
+        }
+        for (int it = it_begin, i = 0; it < it_end; ++it, ++i, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&full_bar[s], ((uint32_t)(g / STAGES)) & 1u);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint64_t a_hi = KCH == 64 ? make_sw128_kmajor_desc(st) : make_sw64_kmajor_desc(st);
+          const uint64_t a_lo = KCH == 64 ? make_sw128_kmajor_desc(st + S::T_BYTES) : make_sw64_kmajor_desc(st + S::T_BYTES);
+          const uint64_t w_hi = KCH == 64 ? make_sw128_kmajor_desc(st + 2 * S::T_BYTES) : make_sw64_kmajor_desc(st + 2 * S::T_BYTES);
+          const uint64_t w_lo = KCH == 64 ? make_sw128_kmajor_desc(st + 3 * S::T_BYTES) : make_sw64_kmajor_desc(st + 3 * S::T_BYTES);
+#pragma unroll
+          for (int k = 0; k < KCH / 16; ++k) {
+            const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
+            umma_f16_2sm(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_hi, k), idesc, first);
+            umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, first);
+            umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
+          }
+          umma_commit_2sm(&empty_bar[s]);
+        }
+        umma_commit_2sm(tmem_full_bar);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, grp = (warp - 4) >> 2, epi_groups = n_epi_warps >> 2;
+    const float unscale = p.amax_bits ? p.unscale * tc_dyn_unscale(__ldg(p.amax_bits)) : p.unscale;
+    const uint32_t empty_addr = leader_bar_addr(tmem_empty_bar);
+    int tl = 0;
+    for (int t = first_tile; t < n_tiles_total; t += tile_step, ++tl) {
+      const int mp = t % sch.m_pairs, r = t / sch.m_pairs, ny = r % sch.n_tiles, z = r / sch.n_tiles;
+      const int m0 = (mp * 2 + (int)rank) * 128, n0 = ny * N_TILE;
+      const TcRow row = tc_decode_row(p, m0 + q * 32 + lane);
+      mbar_wait(tmem_full_bar, (uint32_t)tl & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = grp; c < N_TILE / 32; c += epi_groups) {
+        uint32_t v[32], x[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
+        tmem_ld_wait();
+        const int n = n0 + c * 32;
+        if (!row.valid || n >= p.N) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * unscale;
+        tc_store_chunk(p, row, n, f, z);
+      }
+      tc_fence_before();                                        // this warp's TMEM reads are complete
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(empty_addr);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- packing kernels
 namespace {
 
@@ -355,6 +502,24 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
   using S = TcSmem2<STAGES, KCH>;
   auto kern = tc_gemm2_kernel<STAGES, KCH>;
   AAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  static const bool persistent = getenv("AAE_TC_NOPERSIST") == nullptr;
+  if (persistent) {
+    TcTileSched sch;
+    sch.m_pairs = (int)((grid.x + 1) / 2); sch.n_tiles = (int)grid.y; sch.splits = (int)grid.z;
+    const int tiles = sch.m_pairs * sch.n_tiles * sch.splits;
+    static int pair_slots = 0;                       // CTA pairs that can be resident at once (one per SM pair)
+    if (pair_slots == 0) {
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      pair_slots = std::max(1, sms / 2);
+    }
+    auto pk = tc_gemm2p_kernel<STAGES, KCH>;
+    AAE_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    pk<<<dim3(2u * (unsigned)std::min(tiles, pair_slots)), tc_block_threads(), S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w2_hi, L.tm_w2_lo, L.gp, sch);
+    AAE_LAUNCH_OK();
+    return AAE_OK;
+  }
   grid.x = (grid.x + 1) & ~1u;   // whole CTA pairs
   kern<<<grid, tc_block_threads(), S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w2_hi, L.tm_w2_lo, L.gp);
   AAE_LAUNCH_OK();

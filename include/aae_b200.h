@@ -148,7 +148,13 @@ AAE_API int aae_bootstrap_l2_loss(const float* x_dev, const float* target_dev, i
 
 /* ---------------------------------------------------------------- Training step ------------
  * Replaces sess.run(train_op): encoder fwd, decoder fwd, bootstrapped L2, backward, TF-Adam
- * (auto_pose/ae/ae_train.py:128, auto_pose/ae/ae_factory.py:79-95). */
+ * (auto_pose/ae/ae_train.py:128, auto_pose/ae/ae_factory.py:79-95).
+ * The arithmetic follows the handles: encoder and decoder must have been created with the same
+ * aae_precision.  AAE_PREC_FP32_SIMT runs every contraction as fp32 FMA chains; AAE_PREC_TC_SPLIT
+ * runs the forward pass, the data gradients and the weight gradients of all convs with Cin >= 128
+ * as tcgen05 GEMMs (split-fp16 x3, gradients re-scaled per tensor and per step by a power of two),
+ * the two dense layers and conv1's weight gradient as fp32 kernels; parameters, Adam state and
+ * the gradients returned by aae_trainer_get_grads are fp32 in the reference layouts either way. */
 AAE_API int aae_trainer_create(aae_encoder* enc, aae_decoder* dec, int bootstrap_ratio, float learning_rate,
                                float beta1, float beta2, float epsilon, aae_trainer** out);
 AAE_API int aae_trainer_destroy(aae_trainer* h);
