@@ -115,8 +115,15 @@ class TrainOp(Tensor):
                 raise NotImplementedError("NORM_REGULARIZE > 0 is not part of the fused training step")
             h = C.c_void_p()
             with torch.cuda.device(dev):
-                _lib.check(_lib.lib().aae_trainer_create(enc.handle(device), dec.handle(device), dec._bootstrap_ratio, *self._hp,
-                                                         C.byref(h)), "trainer create")
+                eh, dh = enc.handle(device), dec.handle(device)       # settles automatic precisions
+                st = -3 if enc.precision != dec.precision else _lib.lib().aae_trainer_create(eh, dh, dec._bootstrap_ratio, *self._hp, C.byref(h))
+                if st == -3 and (enc._auto_precision or dec._auto_precision or enc.precision != dec.precision) and \
+                        (enc.precision, dec.precision) != (_lib.PREC_FP32_SIMT, _lib.PREC_FP32_SIMT):
+                    # a geometry the tensor-core trainer is not built for: the fp32 CUDA-core trainer handles every geometry
+                    enc.set_precision(_lib.PREC_FP32_SIMT)
+                    dec.set_precision(_lib.PREC_FP32_SIMT)
+                    st = _lib.lib().aae_trainer_create(enc.handle(device), dec.handle(device), dec._bootstrap_ratio, *self._hp, C.byref(h))
+                _lib.check(st, "trainer create")
             self._trainers[dev] = h
         return self._trainers[dev]
 

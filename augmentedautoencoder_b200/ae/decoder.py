@@ -49,10 +49,10 @@ class Decoder(_DeviceModule):
             base = scoped("conv2d_%d" % (k0 + j))
             var_shapes.append((base + "/kernel", (self._kernel_size, self._kernel_size, cin, f), base + "/bias", (f,)))
             cin = f
-        # same default as the encoder: tensor cores for inference, fp32 CUDA cores for training
+        # same default as the encoder: tensor cores unless precision=_lib.PREC_FP32_SIMT is asked for
         self._auto_precision = precision is None
         if precision is None:
-            precision = _lib.PREC_FP32_SIMT if is_training else _lib.PREC_TC_SPLIT
+            precision = _lib.PREC_TC_SPLIT
         self.precision = int(precision)
         # the C ABI takes the encoder-order filters/strides and reverses them itself (aae_net_cfg)
         self._init_module((h, w, c, list(reversed(self._num_filters)), list(reversed(self._strides)), self._kernel_size,

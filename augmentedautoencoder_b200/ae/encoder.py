@@ -109,6 +109,18 @@ class _DeviceModule:
             self._upload(dev, h)
         return self._handles[dev]
 
+    def set_precision(self, precision):
+        """Re-create the device handles with another aae_precision (weights are kept; device-side values are read back first)."""
+        precision = int(precision)
+        if precision == self.precision:
+            return
+        if self._handles:
+            self.get_weights()
+        self.close()
+        self.precision = precision
+        self._auto_precision = False
+        self._cfg_args = self._cfg_args[:-1] + (precision,)
+
     def close(self):
         for h in self._handles.values():
             self._destroy(h)
@@ -142,10 +154,11 @@ class Encoder(_DeviceModule):
         h, w, c = shape[1:]
         self._in_shape = (h, w, c)
         self.max_batch = int(max_batch)
-        # default: tensor cores for inference (fp32-grade split-fp16 arithmetic), the fp32 CUDA-core path for training
+        # default: tensor cores (fp32-grade split-fp16 arithmetic) for inference and training; precision=_lib.PREC_FP32_SIMT
+        # selects the fp32 CUDA-core path (exact fp32 operation order; ~10x slower)
         self._auto_precision = precision is None
         if precision is None:
-            precision = _lib.PREC_FP32_SIMT if is_training else _lib.PREC_TC_SPLIT
+            precision = _lib.PREC_TC_SPLIT
         self.precision = int(precision)
         var_shapes = []
         cin, hh, ww = c, h, w

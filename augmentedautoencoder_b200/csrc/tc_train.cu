@@ -524,9 +524,33 @@ __global__ void rearrange_sep_wgrad_kernel(const float* __restrict__ in, int cin
   }
 }
 
-// decoder unit: merged weights Wm [9][cin][n4] -> dgrad operand [cin][9 * gN] with the taps flipped, columns >= n4 zero
+// 8 consecutive fp32 -> (hi, lo) fp16, one 16-byte store each
+__device__ __forceinline__ void split_store8(const float (&v)[8], float scale, __half* hi, __half* lo) {
+  uint32_t hh[4], ll[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) split_f16x2(v[2 * t] * scale, v[2 * t + 1] * scale, hh[t], ll[t]);
+  *reinterpret_cast<uint4*>(hi) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+  *reinterpret_cast<uint4*>(lo) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+
+// decoder unit: merged weights Wm [9][cin][n4] -> dgrad operand [cin][9 * gN] with the taps flipped, columns >= n4 zero.
+// One thread per 8 consecutive columns (n4 % 8 == 0) or per column (the padded output layer).
 __global__ void pack_dec_dgrad_kernel(const float* __restrict__ wm, int cin, int n4, int gN, float scale, __half* __restrict__ hi,
                                       __half* __restrict__ lo) {
+  if (n4 % 8 == 0 && gN == n4) {
+    const int g8 = gN / 8;
+    const long long total = (long long)cin * 9 * g8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int n = (int)(i % g8) * 8;
+      long long r = i / g8;
+      const int t = (int)(r % 9);
+      const int ci = (int)(r / 9);
+      float v[8];
+      load8(wm + ((long long)(8 - t) * cin + ci) * n4 + n, v);
+      split_store8(v, scale, hi + i * 8, lo + i * 8);
+    }
+    return;
+  }
   const long long total = (long long)cin * 9 * gN;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i % gN);
@@ -542,22 +566,26 @@ __global__ void pack_dec_dgrad_kernel(const float* __restrict__ wm, int cin, int
 }
 
 // encoder unit: W HWIO [5][5][cin][cout] -> dgrad operand [(py,px,ci)][9 * cout]; tap (ty,tx) of the 3x3 window over dY
-// carries kernel element (3 - 2ty + py, 3 - 2tx + px) when that lies inside the 5x5 kernel
+// carries kernel element (3 - 2ty + py, 3 - 2tx + px) when that lies inside the 5x5 kernel.  8 output channels per thread.
 __global__ void pack_enc_dgrad_kernel(const float* __restrict__ w, int cin, int cout, float scale, __half* __restrict__ hi,
                                       __half* __restrict__ lo) {
-  const long long total = 4LL * cin * 9 * cout;
+  const int c8 = cout / 8;
+  const long long total = 4LL * cin * 9 * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % cout);
-    long long r = i / cout;
+    const int co = (int)(i % c8) * 8;
+    long long r = i / c8;
     const int t = (int)(r % 9); r /= 9;
     const int ci = (int)(r % cin);
     const int cls = (int)(r / cin);
     const int kh = 3 - 2 * (t / 3) + (cls >> 1), kw = 3 - 2 * (t % 3) + (cls & 1);
-    const float v = (kh >= 0 && kh < 5 && kw >= 0 && kw < 5) ? w[(((long long)kh * 5 + kw) * cin + ci) * cout + co] * scale : 0.f;
-    __half a, d;
-    split_f16(v, a, d);
-    hi[i] = a;
-    lo[i] = d;
+    float v[8];
+    if (kh >= 0 && kh < 5 && kw >= 0 && kw < 5) {
+      load8(w + (((long long)kh * 5 + kw) * cin + ci) * cout + co, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    split_store8(v, scale, hi + i * 8, lo + i * 8);
   }
 }
 
@@ -770,7 +798,7 @@ int tc_train_pack_weights(TcTrainPlan* h, int u, const float* w_dev, cudaStream_
   AAE_REQUIRE(u >= 0 && u < (int)h->units.size(), "tc trainer: unit %d out of range", u);
   TcUnit& U = h->units[u];
   if (U.enc) {
-    pack_enc_dgrad_kernel<<<ew_grid(4LL * U.cin * 9 * U.cout), 256, 0, s>>>(w_dev, U.cin, U.cout, W_SCALE, U.dg.w_hi, U.dg.w_lo);
+    pack_enc_dgrad_kernel<<<ew_grid(4LL * U.cin * 9 * U.cout / 8), 256, 0, s>>>(w_dev, U.cin, U.cout, W_SCALE, U.dg.w_hi, U.dg.w_lo);
     AAE_LAUNCH_OK();
     return AAE_OK;
   }

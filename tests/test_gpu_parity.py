@@ -229,7 +229,7 @@ def _small_ae(max_batch=4, hw=16, filters=(4, 8), latent=8):
     strides = (2,) * len(filters)
     x = placeholder(np.float32, [None, hw, hw, 3])
     y = placeholder(np.float32, [None, hw, hw, 3])
-    enc = Encoder(x, latent, list(filters), 5, list(strides), False, is_training=True, max_batch=max_batch)
+    enc = Encoder(x, latent, list(filters), 5, list(strides), False, is_training=True, max_batch=max_batch, precision=0)
     dec = Decoder(y, enc.z, list(reversed(filters)), 5, list(reversed(strides)), "L2", 4, False, False, is_training=True,
                   max_batch=max_batch, n_encoder_convs=len(filters))
     ep = O.make_encoder_params(5, num_filters=filters, in_hw=hw, strides=strides, latent=latent, bias_scale=0.1)
@@ -309,8 +309,9 @@ def test_full_size_training_forward_backward(sess):
     from augmentedautoencoder_b200.ae.session import placeholder
     x = placeholder(np.float32, [None, 128, 128, 3])
     y = placeholder(np.float32, [None, 128, 128, 3])
-    enc = Encoder(x, 128, list(O.NUM_FILTER), 5, list(O.STRIDES), False, is_training=True, max_batch=2)
-    dec = Decoder(y, enc.z, list(reversed(O.NUM_FILTER)), 5, list(reversed(O.STRIDES)), "L2", 4, False, False, is_training=True, max_batch=2)
+    enc = Encoder(x, 128, list(O.NUM_FILTER), 5, list(O.STRIDES), False, is_training=True, max_batch=2, precision=0)
+    dec = Decoder(y, enc.z, list(reversed(O.NUM_FILTER)), 5, list(reversed(O.STRIDES)), "L2", 4, False, False, is_training=True, max_batch=2,
+                  precision=0)
     ep, dp = O.make_encoder_params(42, bias_scale=0.02), O.make_decoder_params(43, bias_scale=0.02)
     enc.load_weights(ep)
     dec.load_weights(dp)
