@@ -853,8 +853,6 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
   }
   for (int u = n_dec; u < n_units; ++u) {
     const int i = nl - 1 - (u - n_dec);          // encoder conv index (E->conv[i], enc_k[i]); i >= 1
-    int is_enc, cin, cout, gh, gw, ndc;
-    tc_train_unit_info(P, u, &is_enc, &cin, &cout, &gh, &gw, &ndc);
     AAE_TRY(tc_train_unit_wgrad(P, u, B, h->enc_k[i].g.p, s));
     AAE_TRY(tc_train_unit_dgrad(P, u, B, s));
     const bool last = u + 1 == n_units;
