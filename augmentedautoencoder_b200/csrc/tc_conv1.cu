@@ -7,8 +7,10 @@
 // the kernel, so the fused path is bit-identical to the reference's float feed), and the row is written in the
 // 128-byte-swizzle K-major canonical layout.  K is padded to 80 = 5 MMA K-steps.  The packed weights ([128][128] K-major,
 // zero beyond k = 75) are TMA-loaded once per CTA and stay resident.  Persistent CTAs loop over 128-pixel tiles with a
-// 2-stage A ring and a double-buffered TMEM accumulator: builders (warps 0-3), epilogue (warps 4-7) and the MMA issuer
-// (warp 8) all overlap.  The epilogue writes conv2's input directly: (hi, lo) fp16, space-to-depth layout.
+// single-stage A buffer and a double-buffered TMEM accumulator: builders (warps 0-3), epilogue (warps 4-11, two per TMEM
+// lane quadrant) and the MMA issuer (warp 12) all overlap.  The epilogue writes conv2's input directly: (hi, lo) fp16, space-to-depth layout.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "tc.cuh"
@@ -25,6 +27,9 @@ constexpr int C1_STAGE = 4 * C1_ATOM;              // hi k[0,64), hi k[64,128), 
 constexpr int C1_STAGES = 1;                       // the build (~0.4k cycles) is short next to the MMAs + epilogue; smem goes to the output staging
 constexpr int C1_OUT_LD = 1040;                    // staged output: 32 blocks of 1 KB (one space-to-depth position each), padded against bank conflicts
 constexpr int C1_KPAD = 80;
+constexpr int C1_EPI_WARPS = 8;                    // two per TMEM lane quadrant (each takes every other 32-channel chunk)
+constexpr int C1_MMA_WARP = 4 + C1_EPI_WARPS;
+constexpr int C1_THREADS = 32 * (C1_MMA_WARP + 1);
 constexpr int C1_PIX_ROWS = 7;                     // input rows feeding two output rows: 2*2 + 3
 constexpr int C1_PIX_LD = 400;                     // (128 + 3 padding pixels) * 3 channels = 393 words, rounded up
 
@@ -34,6 +39,7 @@ struct Conv1Params {
   int OH, OW, N;           // output dims, N = Cout (<= 128)
   int pad_t, pad_l;
   int num_tiles;
+  int out_group;           // consecutive 1 KB output blocks shipped by one bulk store (1, 2, 4, 8): fewer, larger copies vs bank conflicts
   const float* bias;
   float unscale, out_scale, in_scale;
   __half* out_hi;
@@ -61,7 +67,7 @@ __device__ __forceinline__ uint32_t conv1_fetch(const Conv1Params& p, const uint
 }
 
 template <int N, int CIN, bool U8>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(C1_THREADS, 1)
 tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const Conv1Params p) {
   using S = Conv1Smem<N>;
   extern __shared__ uint8_t smem_raw[];
@@ -92,14 +98,14 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
     lut[threadIdx.x] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
   }
   for (int i = threadIdx.x; i < C1_PIX_ROWS * C1_PIX_LD; i += blockDim.x) pix[i] = 0u;   // left/right padding pixels stay zero
-  if (warp == 8 && lane == 0) {
+  if (warp == C1_MMA_WARP && lane == 0) {
     prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo);
     mbar_init(w_full, 1);
     for (int s = 0; s < C1_STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], C1_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  if (warp == C1_MMA_WARP) tmem_alloc<TMEM_COLS>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -199,15 +205,17 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
       if (more) stage(pix);                                   // (its internal barrier orders it after every thread's build of tile i)
       asm volatile("bar.sync 1, 128;" ::: "memory");       // staged rows of tile i+1 visible to all builders
     }
-  } else if (warp < 8) {
+  } else if (warp < C1_MMA_WARP) {
     // ===================== epilogue =====================
     // The 128 pixels x 128 channels of a tile (two output rows of one image) are exactly ONE contiguous 32 KB slab of the
     // consumer's space-to-depth tensor (row oh/2, all 32 column pairs, all four parities) -- per (hi, lo).  Each thread
     // (= pixel) writes its 256 B into a padded shared-memory image of that slab; one thread then ships it with 1 KB bulk
     // stores, i.e. full-line HBM writes instead of 16-byte scattered ones.
-    const int q = warp & 3, r = q * 32 + lane;
+    const int q = warp & 3, half = (warp - 4) >> 2, r = q * 32 + lane;
     const int ow = r % p.OW, dr = r / p.OW;
-    uint8_t* my_hi = out_smem + (ow >> 1) * C1_OUT_LD + (((dr & 1) << 1) | (ow & 1)) * (2 * N);
+    // blocks are grouped G at a time (contiguous, one bulk store per group); 16 bytes of padding after every group
+    const int G = p.out_group, grp_ld = G * 8 * N + 16;
+    uint8_t* my_hi = out_smem + ((ow >> 1) / G) * grp_ld + ((ow >> 1) % G) * (8 * N) + (((dr & 1) << 1) | (ow & 1)) * (2 * N);
     uint8_t* my_lo = my_hi + 32 * C1_OUT_LD;
     for (int i = 0; i < my_tiles; ++i) {
       const int as = i & 1;
@@ -217,10 +225,10 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
       tc_fence_after();
       if (i > 0) {                                   // the previous tile's bulk stores must have finished reading the staging
         if (warp == 4) bulk_wait_read_all();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_EPI_WARPS) : "memory");
       }
 #pragma unroll 1
-      for (int c = 0; c < N / 32; ++c) {
+      for (int c = half; c < N / 32; c += C1_EPI_WARPS / 4) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + c * 32), v);
         tmem_ld_wait();
@@ -241,17 +249,19 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       fence_proxy_async_smem();                      // generic-proxy writes -> visible to the bulk-copy engine
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (warp == 4 && b < p.B) {                    // lane j ships 1 KB block j of the hi and of the lo slab
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_EPI_WARPS) : "memory");
+      if (warp == 4 && b < p.B) {                    // lane j ships group j (G KB) of the hi and of the lo slab
         const long long slab = ((long long)(b * (p.OH >> 1) + (oh0 >> 1)) * (p.OW >> 1)) * (4LL * N);   // elements
-        bulk_store_1d(p.out_hi + slab + (long long)lane * 4 * N, out_smem + lane * C1_OUT_LD, 8 * N);
-        bulk_store_1d(p.out_lo + slab + (long long)lane * 4 * N, out_smem + (32 + lane) * C1_OUT_LD, 8 * N);
+        if (lane < 32 / G) {
+          bulk_store_1d(p.out_hi + slab + (long long)lane * G * 4 * N, out_smem + lane * grp_ld, (uint32_t)(G * 8 * N));
+          bulk_store_1d(p.out_lo + slab + (long long)lane * G * 4 * N, out_smem + 32 * C1_OUT_LD + lane * grp_ld, (uint32_t)(G * 8 * N));
+        }
         bulk_commit_group();
       }
     }
     if (warp == 4) bulk_wait_all();                    // all stores landed before the CTA exits
   } else {
-    // ===================== weight TMA + MMA issuer (warp 8) =====================
+    // ===================== weight TMA + MMA issuer (last warp) =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(w_full, S::W_BYTES);
       tma_load_2d(w_smem, &tm_w_hi, w_full, 0, 0);
@@ -286,7 +296,7 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == C1_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
@@ -358,6 +368,10 @@ int tc_conv1_forward(TcConv1* h, const aae_net_cfg* cfg, const void* crops, int 
   p.pad_t = std::max((p.OH - 1) * 2 + 5 - p.H, 0) / 2;
   p.pad_l = std::max((p.OW - 1) * 2 + 5 - p.W, 0) / 2;
   p.num_tiles = (int)ceil_div((int64_t)B * p.OH * p.OW, 128);
+  {
+    static const int group = [] { const char* e = getenv("AAE_C1_GROUP"); const int g = e ? atoi(e) : 2; return (g == 1 || g == 2 || g == 4 || g == 8) ? g : 2; }();   // measured: 0.25 / 0.22 / 0.28 / 0.28 ms for 1 / 2 / 4 / 8
+    p.out_group = group;
+  }
   p.bias = bias;
   p.in_scale = act_scale; p.out_scale = act_scale; p.unscale = 1.f / (act_scale * w_scale);
   p.out_hi = out_hi; p.out_lo = out_lo;
@@ -365,10 +379,10 @@ int tc_conv1_forward(TcConv1* h, const aae_net_cfg* cfg, const void* crops, int 
   using S = Conv1Smem<128>;
   if (src_u8) {
     AAE_CUDA_OK(cudaFuncSetAttribute(tc_conv1_kernel<128, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    tc_conv1_kernel<128, 3, true><<<grid, 288, S::TOTAL, s>>>(h->tm_hi, h->tm_lo, p);
+    tc_conv1_kernel<128, 3, true><<<grid, C1_THREADS, S::TOTAL, s>>>(h->tm_hi, h->tm_lo, p);
   } else {
     AAE_CUDA_OK(cudaFuncSetAttribute(tc_conv1_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    tc_conv1_kernel<128, 3, false><<<grid, 288, S::TOTAL, s>>>(h->tm_hi, h->tm_lo, p);
+    tc_conv1_kernel<128, 3, false><<<grid, C1_THREADS, S::TOTAL, s>>>(h->tm_hi, h->tm_lo, p);
   }
   AAE_LAUNCH_OK();
   return AAE_OK;
