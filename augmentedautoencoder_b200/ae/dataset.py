@@ -156,3 +156,46 @@ class Dataset(object):
             crop[:, :(x - left)] = 0
             crop[:, (x + w - left):] = 0
         return cv2.resize(crop, resize, interpolation=interpolation)
+
+    # ------------------------------------------------------------------------------------------------ training batches
+    def load_training_images(self, path, bg_path=None):
+        """The cache the reference writes after rendering (``np.savez(current_file_name, train_x=, mask_x=, train_y=)``,
+        dataset.py:101-113) and, optionally, the background image stack (``.npy``, dataset.py:229-255)."""
+        data = np.load(path)
+        self.train_x, self.mask_x, self.train_y = data["train_x"].astype(np.uint8), data["mask_x"], data["train_y"].astype(np.uint8)
+        self.noof_training_imgs = len(self.train_x)
+        if bg_path is not None:
+            self.bg_imgs = np.load(bg_path).astype(np.uint8)
+            self.noof_bg_imgs = len(self.bg_imgs)
+
+    @lazy_property
+    def _aug(self):
+        from .augment import Augmenter
+        code = self._kw.get("code")
+        if code is None:
+            raise NotImplementedError("no [Augmentation] CODE in the dataset arguments")
+        return Augmenter(code, self.shape, seed=self._kw.get("seed"))
+
+    def batch_device(self, batch_size, device=None):
+        """Dataset.batch (dataset.py:456-495) with the image work on the GPU: draws the rendering / background indices like the
+        reference, uploads the uint8 images once and returns (x, y) float32 CUDA tensors in [0, 1]."""
+        import torch
+        for name in ("train_x", "mask_x", "train_y", "bg_imgs"):
+            if not hasattr(self, name):
+                raise RuntimeError("Dataset.%s is not loaded (load_training_images / set the arrays)" % name)
+        if eval(str(self._kw.get("realistic_occlusion", "False"))) or eval(str(self._kw.get("square_occlusion", "False"))):
+            raise NotImplementedError("REALISTIC_OCCLUSION / SQUARE_OCCLUSION are off in the template cfg and not supported")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        idx = np.random.choice(len(self.train_x), batch_size, replace=False)
+        idx_bg = np.random.choice(len(self.bg_imgs), batch_size, replace=False)
+        x = torch.from_numpy(self.train_x[idx]).to(dev, non_blocking=True)
+        m = torch.from_numpy(np.ascontiguousarray(self.mask_x[idx]).astype(np.uint8)).to(dev, non_blocking=True)
+        bg = torch.from_numpy(self.bg_imgs[idx_bg]).to(dev, non_blocking=True)
+        y = torch.from_numpy(self.train_y[idx]).to(dev, non_blocking=True)
+        xf = self._aug.augment_device(x, m, bg)
+        return xf, y.to(torch.float32) / 255.0
+
+    def batch(self, batch_size):
+        """numpy (batch_x, batch_y) like the reference's ``Dataset.batch``."""
+        x, y = self.batch_device(batch_size)
+        return x.cpu().numpy(), y.cpu().numpy()

@@ -498,6 +498,24 @@ extern "C" int aae_topk_merge(const float* scores_dev, const int32_t* idx_dev, i
   return launch_topk_merge(scores_dev, idx_dev, n_shards, batch, k, scores_out_dev, idx_out_dev, (cudaStream_t)stream);
 }
 
+// ============================================================================ training input pipeline
+extern "C" int aae_augment_batch(const uint8_t* x_dev, const uint8_t* mask_dev, const uint8_t* bg_dev, int batch, int h, int w, int c,
+                                 const int32_t* geom_dev, const uint8_t* lut_dev, const uint16_t* bilinear_tab_dev, const uint8_t* row_cell_dev,
+                                 const uint8_t* col_cell_dev, int low_w, const int32_t* blur_kernel_q8, const float* u8_to_float_dev,
+                                 uint8_t* tmp_dev, uint8_t* out_u8_dev, float* out_f32_dev, void* stream) {
+  AAE_REQUIRE(x_dev && mask_dev && bg_dev && geom_dev && lut_dev && bilinear_tab_dev && row_cell_dev && col_cell_dev && tmp_dev, "null argument");
+  AAE_REQUIRE(out_u8_dev || out_f32_dev, "no output requested");
+  AAE_REQUIRE(!out_f32_dev || u8_to_float_dev, "out_f32_dev needs u8_to_float_dev");
+  AAE_REQUIRE(batch >= 1 && h >= 1 && w >= 1 && low_w >= 1, "bad geometry");
+  if (blur_kernel_q8) {
+    int sum = 0;
+    for (int i = 0; i < 5; ++i) sum += blur_kernel_q8[i];
+    AAE_REQUIRE(sum == 256, "blur kernel must sum to 256 (8 fractional bits), got %d", sum);
+  }
+  return launch_augment(x_dev, mask_dev, bg_dev, batch, h, w, c, geom_dev, lut_dev, bilinear_tab_dev, row_cell_dev, col_cell_dev, low_w,
+                        blur_kernel_q8, u8_to_float_dev, tmp_dev, out_u8_dev, out_f32_dev, (cudaStream_t)stream);
+}
+
 // ============================================================================ decoder
 extern "C" int aae_decoder_create(int device, const aae_net_cfg* cfg, aae_decoder** out) {
   AAE_REQUIRE(out != nullptr, "out is null");

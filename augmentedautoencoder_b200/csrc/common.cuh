@@ -140,6 +140,11 @@ int launch_conv_small_n(const IGemmParams& p, cudaStream_t stream);
 // p.K = number of pixels, p.Bm = dY [pixels, N<=3]; partial: [chunks, taps*SC*N]
 int launch_wgrad_small_n(const IGemmParams& p, int chunks, float* partial, cudaStream_t stream);
 
+// ---- training input pipeline (augment.cu) --------------------------------------------------
+int launch_augment(const uint8_t* x, const uint8_t* mask, const uint8_t* bg, int B, int H, int W, int C, const int32_t* geom, const uint8_t* lut,
+                   const unsigned short* tab, const uint8_t* row_cell, const uint8_t* col_cell, int low_w, const int32_t* blur_q8, const float* to_float,
+                   uint8_t* tmp, uint8_t* out_u8, float* out_f32, cudaStream_t s);
+
 // ---- codebook ------------------------------------------------------------------------------
 int launch_l2_normalize(const float* z, int B, int J, float* out, cudaStream_t stream);
 

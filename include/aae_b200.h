@@ -146,6 +146,21 @@ AAE_API int aae_decoder_forward(aae_decoder* h, const float* z_dev, int batch, f
 AAE_API int aae_bootstrap_l2_loss(const float* x_dev, const float* target_dev, int batch, int numel_per_sample,
                                   int bootstrap_ratio, float* loss_out_dev, float* grad_out_dev, void* stream);
 
+/* ---------------------------------------------------------------- Training input pipeline ---
+ * Dataset.batch on the device (auto_pose/ae/dataset.py:456-495): x[mask] = bg[mask], then the imgaug chain of the training
+ * cfg (auto_pose/ae/cfg/train_template.cfg:26-37) with every random draw made by the caller:
+ *   geom_dev   [B][4 + 2W + 2H] int32 per image: flags (1 affine, 2 coarse dropout, 4 blur), dropout keep bits (low, high
+ *              32 bits over the low_h x low_w cells, row-major), 0, then cv2.warpAffine's fixed-point tables adelta[W],
+ *              bdelta[W], X0[H], Y0[H] (10 fractional bits, rounding offset included)
+ *   lut_dev    [B][C][256] uint8: the composed Add / Invert / Multiply / Multiply / ContrastNormalization table
+ *   bilinear_tab_dev [1024][4] uint16: OpenCV's INTER_LINEAR weight table (rows sum to 32768);  row_cell_dev [H] / col_cell_dev [W]: cv2.resize
+ *              INTER_NEAREST index maps of the dropout mask;  blur_kernel_q8: 5 host ints summing to 256 (NULL: no blur);
+ *   u8_to_float_dev [256]: value / 255.  tmp_dev: [B,H,W,C] uint8 scratch.  out_u8_dev / out_f32_dev: either may be NULL. */
+AAE_API int aae_augment_batch(const uint8_t* x_dev, const uint8_t* mask_dev, const uint8_t* bg_dev, int batch, int h, int w, int c,
+                              const int32_t* geom_dev, const uint8_t* lut_dev, const uint16_t* bilinear_tab_dev,
+                              const uint8_t* row_cell_dev, const uint8_t* col_cell_dev, int low_w, const int32_t* blur_kernel_q8,
+                              const float* u8_to_float_dev, uint8_t* tmp_dev, uint8_t* out_u8_dev, float* out_f32_dev, void* stream);
+
 /* ---------------------------------------------------------------- Training step ------------
  * Replaces sess.run(train_op): encoder fwd, decoder fwd, bootstrapped L2, backward, TF-Adam
  * (auto_pose/ae/ae_train.py:128, auto_pose/ae/ae_factory.py:79-95).
