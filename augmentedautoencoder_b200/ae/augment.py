@@ -220,37 +220,52 @@ class Augmenter(object):
 
     # -- host: pack the draws into the two device buffers ------------------------------------------------------------
     def pack(self, P):
+        """-> geom int32 [B, 4 + 2W + 2H], lut uint8 [B, C, 256] (include/aae_b200.h: aae_augment_batch); vectorised over the batch."""
         B = len(P["affine_on"])
         H, W, C_ = self.h, self.w, self.c
         geom = np.zeros((B, 4 + 2 * W + 2 * H), np.int32)
         blur = bool(self.sigma > 1e-3)
-        weights = (1 << np.arange(self.low[0] * self.low[1], dtype=np.uint64))
-        for b in range(B):
-            flags = (FLAG_AFFINE if P["affine_on"][b] else 0) | (FLAG_DROP if P["drop_on"][b] else 0) | (FLAG_BLUR if (P["blur_on"][b] and blur) else 0)
-            keep = int((P["drop_keep"][b].reshape(-1).astype(np.uint64) * weights).sum())
-            geom[b, 0] = flags
-            geom[b, 1] = np.array(keep & 0xFFFFFFFF, np.uint32).astype(np.int32)
-            geom[b, 2] = np.array(keep >> 32, np.uint32).astype(np.int32)
-            if P["affine_on"][b]:
-                a, bd, x0, y0 = affine_tables(P["affine_M"][b], H, W)
-                geom[b, 4:4 + W], geom[b, 4 + W:4 + 2 * W] = a, bd
-                geom[b, 4 + 2 * W:4 + 2 * W + H], geom[b, 4 + 2 * W + H:] = x0, y0
-        lut = np.empty((B, C_, 256), np.uint8)
-        for b in range(B):
-            for c in range(C_):
-                t = _IDENT
-                if P["add_on"][b]:
-                    t = _lut_add(P["add_val"][b, c])[t]
-                if P["invert_on"][b] and P["invert_ch"][b, c]:
-                    t = (255 - t).astype(np.uint8)
-                if P["mul1_on"][b]:
-                    t = _lut_mul(P["mul1_val"][b, c])[t]
-                if P["mul2_on"][b]:
-                    t = _lut_mul(P["mul2_val"][b, c])[t]
-                if P["contrast_on"][b]:
-                    t = _lut_contrast(P["contrast_val"][b, c])[t]
-                lut[b, c] = t
-        return geom, lut
+        geom[:, 0] = (P["affine_on"].astype(np.int32) * FLAG_AFFINE) | (P["drop_on"].astype(np.int32) * FLAG_DROP) | \
+                     ((P["blur_on"] & blur).astype(np.int32) * FLAG_BLUR)
+        weights = (np.uint64(1) << np.arange(self.low[0] * self.low[1], dtype=np.uint64))
+        keep = (P["drop_keep"].reshape(B, -1).astype(np.uint64) * weights[None, :]).sum(1, dtype=np.uint64)
+        geom[:, 1] = (keep & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.int32)
+        geom[:, 2] = (keep >> np.uint64(32)).astype(np.uint32).view(np.int32)
+        on = np.nonzero(P["affine_on"])[0]
+        if len(on):
+            # cv2.warpAffine: invert the forward matrix in double, then 10-bit fixed-point column / row tables (affine_tables, batched)
+            M = np.array(P["affine_M"][on], np.float64)
+            D = M[:, 0, 0] * M[:, 1, 1] - M[:, 0, 1] * M[:, 1, 0]
+            D = np.where(D != 0, 1.0 / np.where(D != 0, D, 1.0), 0.0)
+            a11, a22 = M[:, 1, 1] * D, M[:, 0, 0] * D
+            m01, m10 = M[:, 0, 1] * -D, M[:, 1, 0] * -D
+            b1 = -a11 * M[:, 0, 2] - m01 * M[:, 1, 2]
+            b2 = -m10 * M[:, 0, 2] - a22 * M[:, 1, 2]
+            xs, ys = np.arange(W, dtype=np.float64)[None, :], np.arange(H, dtype=np.float64)[None, :]
+            geom[on, 4:4 + W] = np.rint(a11[:, None] * xs * 1024.0).astype(np.int32)
+            geom[on, 4 + W:4 + 2 * W] = np.rint(m10[:, None] * xs * 1024.0).astype(np.int32)
+            geom[on, 4 + 2 * W:4 + 2 * W + H] = (np.rint((m01[:, None] * ys + b1[:, None]) * 1024.0) + 16).astype(np.int32)
+            geom[on, 4 + 2 * W + H:] = (np.rint((a22[:, None] * ys + b2[:, None]) * 1024.0) + 16).astype(np.int32)
+        # value ops: one uint8 -> uint8 table per (image, channel), composed in the cfg's order
+        ramp = np.arange(256, dtype=np.float32)[None, None, :]
+        t = np.broadcast_to(np.arange(256, dtype=np.int32)[None, None, :], (B, C_, 256)).copy()
+
+        base = (np.arange(B * C_, dtype=np.int32) * 256).reshape(B, C_, 1)
+
+        def apply(table, on_b):                                  # table [B, C, 256]; on_b [B] (or [B, C]) bool
+            if not on_b.any():
+                return t
+            nxt = np.ascontiguousarray(table, dtype=np.int32).reshape(-1)[base + t]
+            sel = on_b[:, None, None] if on_b.ndim == 1 else on_b[:, :, None]
+            return np.where(sel, nxt, t)
+
+        t = apply(np.clip(np.arange(256, dtype=np.int32)[None, None, :] + P["add_val"].astype(np.int32)[:, :, None], 0, 255), P["add_on"])
+        t = apply(np.broadcast_to(255 - np.arange(256, dtype=np.int32)[None, None, :], (B, C_, 256)), P["invert_on"][:, None] & P["invert_ch"])
+        t = apply(np.clip(ramp * P["mul1_val"].astype(np.float32)[:, :, None], 0, 255).astype(np.uint8), P["mul1_on"])
+        t = apply(np.clip(ramp * P["mul2_val"].astype(np.float32)[:, :, None], 0, 255).astype(np.uint8), P["mul2_on"])
+        t = apply(np.clip(np.float32(127) + P["contrast_val"].astype(np.float32)[:, :, None] * (ramp - np.float32(127)), 0, 255).astype(np.uint8),
+                  P["contrast_on"])
+        return geom, t.astype(np.uint8)
 
     # -- device ------------------------------------------------------------------------------------------------------
     def _constants(self, dev):
