@@ -40,7 +40,7 @@ MATCH_BYTES = N_ROWS * LATENT * 4 + BATCH * LATENT * 4 + BATCH * 8
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures of this exact workload
 # (profiles/r01_ncu_*.txt; precision=tc, batch 256).  Algorithmic bytes beside them: conv2 = 537 MB (hi,lo) input + 3.3 MB
 # weights + 268 MB output = 808 MB; match = 47.36 MB.
-NCU_TRAFFIC = {"tc": {"conv1": 12688384 + 477692672, "conv2": 551194880 + 236450048, "match": 47414272 + 1536}}
+NCU_TRAFFIC = {"tc": {"conv1": 12688384 + 477692672, "conv2": 558148608 + 237978368, "match": 47414272 + 1536}}
 
 
 def peaks():
