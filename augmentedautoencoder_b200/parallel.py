@@ -57,7 +57,7 @@ class ShardedCodebook:
     embedding: the FULL [N, J] float32 table (every rank slices its own rows; a loader that only reads its rows can pass
     ``row_range`` and the slice instead)."""
 
-    def __init__(self, embedding, num_cyclo=36, max_batch=256, precision=_lib.PREC_FP32_SIMT, device=None, group=None,
+    def __init__(self, embedding, num_cyclo=36, max_batch=256, precision=None, device=None, group=None,
                  row_range=None, n_rows_total=None):
         self.group = group
         self.rank, self.world = _world(group)
@@ -71,7 +71,10 @@ class ShardedCodebook:
             self.n_total = int(n_rows_total)
             assert emb.shape[0] == self.hi - self.lo
         self.latent = emb.shape[1]
-        self.num_cyclo, self.max_batch, self.precision = int(num_cyclo), int(max_batch), int(precision)
+        # precision=None: the tensor-core match where the latent size allows it, else the fp32 kernels (as ae.codebook.Codebook)
+        self._auto_precision = precision is None
+        self.num_cyclo, self.max_batch = int(num_cyclo), int(max_batch)
+        self.precision = _lib.PREC_TC_SPLIT if precision is None else int(precision)
         self.device = device
         self._local = np.ascontiguousarray(emb)
         self._handle = None
@@ -85,9 +88,13 @@ class ShardedCodebook:
             return
         h = C.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().aae_codebook_create(self.device.index, _lib.ptr(self._local), self._local.shape[0], self.latent,
-                                                      self.num_cyclo, self.lo, self.max_batch, self.precision, C.byref(h)),
-                       "sharded codebook create")
+            st = _lib.lib().aae_codebook_create(self.device.index, _lib.ptr(self._local), self._local.shape[0], self.latent, self.num_cyclo, self.lo,
+                                                self.max_batch, self.precision, C.byref(h))
+            if st == -3 and self._auto_precision and self.precision == _lib.PREC_TC_SPLIT:
+                self.precision = _lib.PREC_FP32_SIMT
+                st = _lib.lib().aae_codebook_create(self.device.index, _lib.ptr(self._local), self._local.shape[0], self.latent, self.num_cyclo,
+                                                    self.lo, self.max_batch, self.precision, C.byref(h))
+            _lib.check(st, "sharded codebook create")
         self._handle = h
 
     def _local_match(self, z, k, upright):

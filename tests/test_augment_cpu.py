@@ -104,3 +104,18 @@ def test_sampled_parameters_follow_the_cfg_distributions():
     assert abs(P["drop_keep"].mean() - 0.8) < 0.01
     assert 0.6 <= P["mul1_val"].min() and P["mul1_val"].max() <= 1.4 and (P["mul2_val"] == P["mul2_val"][:, :1]).all()
     assert abs(P["invert_ch"].mean() - 0.2) < 0.02
+
+
+def test_subset_chains_and_unsupported_variants():
+    aug = A.Augmenter("Sequential([Sometimes(1.0, Add((10, 10))), Multiply((2.0, 2.0))])", seed=0)
+    P = aug.sample(5)
+    assert P["add_on"].all() and P["mul1_on"].all() and not P["affine_on"].any() and not P["blur_on"].any()
+    _, lut = aug.pack(P)
+    want = np.clip((np.clip(np.arange(256) + 10, 0, 255)).astype(np.float32) * np.float32(2.0), 0, 255).astype(np.uint8)
+    assert np.array_equal(lut[0, 0], want) and np.array_equal(lut[4, 2], want)
+    with pytest.raises(NotImplementedError):
+        A.Augmenter("Sequential([Sometimes(0.5, Add((1, 2)))], random_order=True)")
+    with pytest.raises(NotImplementedError):
+        A.Augmenter("Sequential([Sometimes(0.5, GaussianBlur(2.0))])")
+    with pytest.raises(NotImplementedError):
+        A.Augmenter("Sequential([Sometimes(0.5, CoarseDropout(p=0.1, size_percent=0.5))])")
