@@ -119,3 +119,19 @@ def test_subset_chains_and_unsupported_variants():
         A.Augmenter("Sequential([Sometimes(0.5, GaussianBlur(2.0))])")
     with pytest.raises(NotImplementedError):
         A.Augmenter("Sequential([Sometimes(0.5, CoarseDropout(p=0.1, size_percent=0.5))])")
+
+
+def test_packed_affine_tables_match_the_restatement_per_image():
+    aug = A.Augmenter(TEMPLATE_CODE, seed=9)
+    P = aug.sample(32)
+    P["affine_M"][3] = [[0.9, 0.2, 5.3], [-0.15, 1.1, -3.7]]          # a general matrix, not only scalings
+    P["affine_on"][3] = True
+    geom, _ = aug.pack(P)
+    H = W = 128
+    for b in range(32):
+        if not P["affine_on"][b]:
+            assert not geom[b, 4:].any()
+            continue
+        ad, bd, x0, y0 = AO.affine_fixed_point(P["affine_M"][b], H, W)
+        assert np.array_equal(geom[b, 4:4 + W], ad) and np.array_equal(geom[b, 4 + W:4 + 2 * W], bd)
+        assert np.array_equal(geom[b, 4 + 2 * W:4 + 2 * W + H], x0) and np.array_equal(geom[b, 4 + 2 * W + H:], y0)
