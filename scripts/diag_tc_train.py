@@ -2,7 +2,6 @@
 loss and every gradient after one forward/backward on the same weights and inputs, then step timing at batch 64."""
 import os
 import sys
-import time
 
 import numpy as np
 import torch

@@ -1,6 +1,5 @@
 """GPU parity tests: the CUDA path (through the ctypes -> C ABI boundary) against the CPU oracle on the same seeded
 inputs.  Tolerances: indices bit-exact; cosine scores |d| <= 1e-5 (BASELINE.json north_star)."""
-import os
 
 import numpy as np
 import pytest
