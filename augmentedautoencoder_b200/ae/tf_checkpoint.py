@@ -200,8 +200,9 @@ def read_tf_checkpoint(prefix, names=None, verify_crc=False):
     return out
 
 
-def write_tf_checkpoint(prefix, tensors):
-    """Write {name: array} as a single-shard tensor bundle that ``tf.train.Saver.restore`` reads (and ``read_tf_checkpoint``)."""
+def write_tf_checkpoint(prefix, tensors, entries_per_block=None):
+    """Write {name: array} as a single-shard tensor bundle that ``tf.train.Saver.restore`` reads (and ``read_tf_checkpoint``).
+    entries_per_block: split the index into several data blocks (TensorFlow starts a new block every 4 KB; None = one block)."""
     os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
     items = sorted(((k.encode("utf-8"), np.asarray(v)) for k, v in tensors.items()), key=lambda kv_: kv_[0])   # (ascontiguousarray would promote 0-d)
     data, kv = bytearray(), []
@@ -239,9 +240,14 @@ def write_tf_checkpoint(prefix, tensors):
         return off, len(blk)
 
     with open(prefix + ".index", "wb") as f:
-        d_off, d_size = emit(f, block(kv))
+        step = len(kv) if not entries_per_block else max(1, int(entries_per_block))
+        handles = []
+        for a in range(0, len(kv), step):
+            chunk = kv[a:a + step]
+            d_off, d_size = emit(f, block(chunk))
+            handles.append((chunk[-1][0] + b"\x00", _put_varint(d_off) + _put_varint(d_size)))    # separator key >= every key of the block
         m_off, m_size = emit(f, block([]))
-        i_off, i_size = emit(f, block([(kv[-1][0] + b"\x00", _put_varint(d_off) + _put_varint(d_size))], 1))
+        i_off, i_size = emit(f, block(handles, 1))
         footer = _put_varint(m_off) + _put_varint(m_size) + _put_varint(i_off) + _put_varint(i_size)
         f.write(footer + b"\x00" * (40 - len(footer)) + struct.pack("<Q", _MAGIC))
 

@@ -132,6 +132,10 @@ def test_tf_tensor_bundle_round_trip(tmp_path):
     for k, v in tensors.items():
         assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v), k
     assert set(read_tf_checkpoint(prefix, names={"obj/conv2d/bias"})) == {"obj/conv2d/bias"}
+    multi = str(tmp_path / "checkpoints" / "chkpt-30001")           # index split over several data blocks, as TensorFlow does every 4 KB
+    write_tf_checkpoint(multi, tensors, entries_per_block=7)
+    got = read_tf_checkpoint(multi, verify_crc=True)
+    assert set(got) == set(tensors) and all(np.array_equal(got[k], v) for k, v in tensors.items())
     with open(prefix + ".index", "r+b") as f:                      # corrupt the magic -> loud failure
         f.seek(-1, 2)
         f.write(b"\x00")
