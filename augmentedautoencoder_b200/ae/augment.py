@@ -7,8 +7,8 @@ random draws are made here with numpy (same distributions as imgaug's stochastic
 value ops as composed 256-entry tables (include/aae_b200.h).  At the tensor-core trainer's ~10 000 images/s the reference's
 10 Python threads of imgaug would be the bottleneck by more than an order of magnitude.
 
-Supported chain (any subset, in the cfg's order for the value ops; the geometric ops run in the template's order Affine ->
-CoarseDropout -> GaussianBlur before them): Sometimes(p, Affine(scale=(a, b))), Sometimes(p, CoarseDropout(p=, size_percent=)),
+Supported chain: any subset of the template's ops IN THE TEMPLATE'S ORDER (Affine, CoarseDropout, GaussianBlur, Add, Invert,
+Multiply, Multiply, ContrastNormalization; another order raises): Sometimes(p, Affine(scale=(a, b))), Sometimes(p, CoarseDropout(p=, size_percent=)),
 Sometimes(p, GaussianBlur(sigma)), Sometimes(p, Add((a, b), per_channel=)), Sometimes(p, Invert(p, per_channel=True)),
 Sometimes(p, Multiply((a, b), per_channel=)), Sometimes(p, ContrastNormalization((a, b), per_channel=)).  Anything else raises.
 """
@@ -148,6 +148,15 @@ class Augmenter(object):
     def __init__(self, code, shape=(128, 128, 3), seed=None):
         self.h, self.w, self.c = int(shape[0]), int(shape[1]), int(shape[2])
         self.ops = parse_code(code) if isinstance(code, str) else list(code)
+        canon = ["Affine", "CoarseDropout", "GaussianBlur", "Add", "Invert", "Multiply", "Multiply", "ContrastNormalization"]
+        pos = 0
+        for _, op in self.ops:                                  # the kernels apply the ops in the template's order
+            kind = "ContrastNormalization" if op.kind == "LinearContrast" else op.kind
+            while pos < len(canon) and canon[pos] != kind:
+                pos += 1
+            if pos == len(canon):
+                raise NotImplementedError("augmenter order %s is not a sub-sequence of %s" % ([o.kind for _, o in self.ops], canon))
+            pos += 1
         self.rng = np.random.RandomState(seed)
         self.sigma = 0.0
         self.low = (1, 1)
@@ -246,25 +255,26 @@ class Augmenter(object):
             geom[on, 4 + W:4 + 2 * W] = np.rint(m10[:, None] * xs * 1024.0).astype(np.int32)
             geom[on, 4 + 2 * W:4 + 2 * W + H] = (np.rint((m01[:, None] * ys + b1[:, None]) * 1024.0) + 16).astype(np.int32)
             geom[on, 4 + 2 * W + H:] = (np.rint((a22[:, None] * ys + b2[:, None]) * 1024.0) + 16).astype(np.int32)
-        # value ops: one uint8 -> uint8 table per (image, channel), composed in the cfg's order
-        ramp = np.arange(256, dtype=np.float32)[None, None, :]
-        t = np.broadcast_to(np.arange(256, dtype=np.int32)[None, None, :], (B, C_, 256)).copy()
+        # value ops: one uint8 -> uint8 table per (image, channel) = the op chain evaluated on the 256 possible values, every op
+        # with the arithmetic of its imgaug uint8 table (integer add + clip; float32 multiply, clip, truncate)
+        t = np.broadcast_to(np.arange(256, dtype=np.int32)[None, None, :], (B, C_, 256))
+        f127 = np.float32(127)
 
-        base = (np.arange(B * C_, dtype=np.int32) * 256).reshape(B, C_, 1)
+        def sel(on_b, new):
+            m = on_b[:, None, None] if on_b.ndim == 1 else on_b[:, :, None]
+            return np.where(m, new, t)
 
-        def apply(table, on_b):                                  # table [B, C, 256]; on_b [B] (or [B, C]) bool
-            if not on_b.any():
-                return t
-            nxt = np.ascontiguousarray(table, dtype=np.int32).reshape(-1)[base + t]
-            sel = on_b[:, None, None] if on_b.ndim == 1 else on_b[:, :, None]
-            return np.where(sel, nxt, t)
-
-        t = apply(np.clip(np.arange(256, dtype=np.int32)[None, None, :] + P["add_val"].astype(np.int32)[:, :, None], 0, 255), P["add_on"])
-        t = apply(np.broadcast_to(255 - np.arange(256, dtype=np.int32)[None, None, :], (B, C_, 256)), P["invert_on"][:, None] & P["invert_ch"])
-        t = apply(np.clip(ramp * P["mul1_val"].astype(np.float32)[:, :, None], 0, 255).astype(np.uint8), P["mul1_on"])
-        t = apply(np.clip(ramp * P["mul2_val"].astype(np.float32)[:, :, None], 0, 255).astype(np.uint8), P["mul2_on"])
-        t = apply(np.clip(np.float32(127) + P["contrast_val"].astype(np.float32)[:, :, None] * (ramp - np.float32(127)), 0, 255).astype(np.uint8),
-                  P["contrast_on"])
+        if P["add_on"].any():
+            t = sel(P["add_on"], np.clip(t + P["add_val"].astype(np.int32)[:, :, None], 0, 255))
+        inv = P["invert_on"][:, None] & P["invert_ch"]
+        if inv.any():
+            t = sel(inv, 255 - t)
+        for key in ("mul1", "mul2"):
+            if P[key + "_on"].any():
+                t = sel(P[key + "_on"], np.clip(t.astype(np.float32) * P[key + "_val"].astype(np.float32)[:, :, None], 0, 255).astype(np.uint8).astype(np.int32))
+        if P["contrast_on"].any():
+            c = f127 + P["contrast_val"].astype(np.float32)[:, :, None] * (t.astype(np.float32) - f127)
+            t = sel(P["contrast_on"], np.clip(c, 0, 255).astype(np.uint8).astype(np.int32))
         return geom, t.astype(np.uint8)
 
     # -- device ------------------------------------------------------------------------------------------------------

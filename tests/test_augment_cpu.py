@@ -115,6 +115,8 @@ def test_subset_chains_and_unsupported_variants():
     assert np.array_equal(lut[0, 0], want) and np.array_equal(lut[4, 2], want)
     with pytest.raises(NotImplementedError):
         A.Augmenter("Sequential([Sometimes(0.5, Add((1, 2)))], random_order=True)")
+    with pytest.raises(NotImplementedError):                      # value ops in another order than the kernels apply them
+        A.Augmenter("Sequential([Multiply((0.5, 1.5)), Add((1, 2))])")
     with pytest.raises(NotImplementedError):
         A.Augmenter("Sequential([Sometimes(0.5, GaussianBlur(2.0))])")
     with pytest.raises(NotImplementedError):
