@@ -275,7 +275,9 @@ class Augmenter(object):
         if P["contrast_on"].any():
             c = f127 + P["contrast_val"].astype(np.float32)[:, :, None] * (t.astype(np.float32) - f127)
             t = sel(P["contrast_on"], np.clip(c, 0, 255).astype(np.uint8).astype(np.int32))
-        return geom, t.astype(np.uint8)
+        # t may still be the stride-0 broadcast view (no value op fired): astype would keep a permuted memory order, and the
+        # kernel reads raw [B][C][256] memory
+        return np.ascontiguousarray(geom), np.ascontiguousarray(t, dtype=np.uint8)
 
     # -- device ------------------------------------------------------------------------------------------------------
     def _constants(self, dev):
@@ -297,8 +299,12 @@ class Augmenter(object):
         B = x.shape[0]
         P = params if params is not None else self.sample(B)
         geom, lut = self.pack(P)
+        geom, lut = np.ascontiguousarray(geom, dtype=np.int32), np.ascontiguousarray(lut, dtype=np.uint8)
+        if geom.shape != (B, 4 + 2 * self.w + 2 * self.h) or lut.shape != (B, self.c, 256):
+            raise ValueError("augmentation tables have shapes %s / %s for a batch of %d" % (geom.shape, lut.shape, B))
         k = self._constants(dev)
         geom_d, lut_d = torch.from_numpy(geom).to(dev, non_blocking=True), torch.from_numpy(lut).to(dev, non_blocking=True)
+        assert geom_d.is_contiguous() and lut_d.is_contiguous()
         mask8 = mask.to(torch.uint8).contiguous()
         tmp = torch.empty_like(x)
         out_f = torch.empty(x.shape, dtype=torch.float32, device=dev)

@@ -1,4 +1,4 @@
-"""Tensor-core trainer vs the fp32 CUDA-core trainer (itself pinned to the float64 oracle by tests/test_gpu_parity.py):
+"""Tensor-core trainer vs the fp32 CUDA-core trainer (itself pinned to the float64 oracle by tests/test_gpu_a_parity.py):
 loss and every gradient after one forward/backward on the same weights and inputs, then step timing at batch 64."""
 import os
 import sys

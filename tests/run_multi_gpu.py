@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 from augmentedautoencoder_b200 import _lib  # noqa: E402
 from augmentedautoencoder_b200.parallel import ObjectRouter, ShardedCodebook, owner_of_class, split_batch  # noqa: E402
 from oracle import aae_oracle as O  # noqa: E402
-from tests.test_gpu_parity import _codebook, _enc  # noqa: E402
+from tests.test_gpu_a_parity import _codebook, _enc  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)

@@ -137,3 +137,21 @@ def test_packed_affine_tables_match_the_restatement_per_image():
         ad, bd, x0, y0 = AO.affine_fixed_point(P["affine_M"][b], H, W)
         assert np.array_equal(geom[b, 4:4 + W], ad) and np.array_equal(geom[b, 4 + W:4 + 2 * W], bd)
         assert np.array_equal(geom[b, 4 + 2 * W:4 + 2 * W + H], x0) and np.array_equal(geom[b, 4 + 2 * W + H:], y0)
+
+
+@pytest.mark.parametrize("fire", [(), ("add_on",), ("invert_on",), ("contrast_on",), ("mul1_on", "mul2_on")])
+def test_packed_tables_are_c_contiguous_whatever_fires(fire):
+    """The kernel reads geom / lut as raw [B][...] memory: with no value op firing the table is still the stride-0 broadcast
+    of the identity ramp, and a K-order astype of that view is NOT row-major (round-1 regression)."""
+    aug = A.Augmenter(TEMPLATE_CODE, seed=0)
+    P = aug.sample(3)
+    for k in P:
+        if k.endswith("_on"):
+            P[k][:] = k in fire
+    geom, lut = aug.pack(P)
+    assert geom.flags.c_contiguous and lut.flags.c_contiguous and lut.dtype == np.uint8 and geom.dtype == np.int32
+    assert lut.strides == (3 * 256, 256, 1)
+    raw = np.frombuffer(lut.tobytes(order="A"), np.uint8).reshape(3, 3, 256)      # memory order, as the device sees it
+    assert np.array_equal(raw, lut)
+    if not fire:
+        assert np.array_equal(raw, np.broadcast_to(np.arange(256, dtype=np.uint8), (3, 3, 256)))

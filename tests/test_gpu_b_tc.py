@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import aae_oracle as O
-from tests.test_gpu_parity import COS_TOL, _codebook, _enc, sess  # noqa: F401
+from tests.test_gpu_a_parity import COS_TOL, _codebook, _enc, sess  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import aae_oracle as O
-from tests.test_gpu_parity import _codebook, _enc, sess  # noqa: F401
+from tests.test_gpu_a_parity import _codebook, _enc, sess  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
