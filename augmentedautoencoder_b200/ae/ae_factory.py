@@ -35,16 +35,17 @@ class Queue(object):
         self._batch_size = batch_size
         self._source = source or (lambda n: dataset.batch(n))
         shape = (None,) + tuple(dataset.shape)
-        self._cache = None
         self.x = Tensor("queue_x", shape, np.float32, lambda ctx: self._pull(ctx)[0])
         self.y = Tensor("queue_y", shape, np.float32, lambda ctx: self._pull(ctx)[1])
 
     def _pull(self, ctx):
-        key = id(ctx)
-        if self._cache is None or self._cache[0] != key:
+        """One dequeue per ``Session.run``: x and y fetched in the same run see the same batch, the next run pulls the next
+        one.  The batch lives in the run's own memo (not keyed by ``id(ctx)``: a freed context's address is reused)."""
+        key = ("queue_batch", id(self))            # the Queue outlives every RunContext, so its id is stable
+        if key not in ctx.memo:
             x, y = self._source(self._batch_size)
-            self._cache = (key, (S.to_device_input(x, ctx.session.device), S.to_device_input(y, ctx.session.device)))
-        return self._cache[1]
+            ctx.memo[key] = (S.to_device_input(x, ctx.session.device), S.to_device_input(y, ctx.session.device))
+        return ctx.memo[key]
 
     def start(self, session):
         pass
@@ -241,14 +242,25 @@ class Saver(object):
             f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (os.path.basename(prefix), os.path.basename(prefix)))
         return prefix
 
-    def restore(self, session, path):
-        """path: ``chkpt-<step>.npz`` or the prefix of a TensorFlow checkpoint (``.../chkpt-30000``)."""
+    def restore(self, session, path, strict=True):
+        """path: ``chkpt-<step>.npz`` or the prefix of a TensorFlow checkpoint (``.../chkpt-30000``).  As with
+        ``tf.train.Saver.restore`` (NotFoundError), every variable of every module must be in the checkpoint: a checkpoint of
+        another experiment scope must not leave seeded weights and an all-zero codebook behind silently.  ``strict=False``
+        restores what is there (e.g. a training checkpoint written by a Saver that did not include the codebook)."""
         if path.endswith(".npz"):
             data = np.load(path)
             weights = {k: data[k] for k in data.files}
         else:
             from .tf_checkpoint import read_tf_checkpoint
             weights = read_tf_checkpoint(path)
+        missing = []
+        for m in self._modules:
+            if isinstance(m, Codebook):
+                missing += [v.name for v in ([m.embedding_normalized] + ([m.embed_obj_bbs_var] if m.embed_bb else [])) if v.name not in weights]
+            else:
+                missing += [n for n in m.variable_names if n not in weights and "/".join(n.split("/")[-2:]) not in weights]
+        if missing and strict:
+            raise KeyError("%s does not hold: %s" % (path, ", ".join(missing)))
         for m in self._modules:
             if isinstance(m, Codebook):
                 if m.embedding_normalized.name in weights:
@@ -257,7 +269,7 @@ class Saver(object):
                     m.embed_obj_bbs_var.assign(weights[m.embed_obj_bbs_var.name])
                     m.embed_obj_bbs_values = None
             else:
-                m.load_weights(weights)
+                m.load_weights(weights, strict=strict)
         if self._global_step is not None and self._global_step.name in weights:
             self._global_step._host = np.asarray(weights[self._global_step.name], dtype=np.int64)
 

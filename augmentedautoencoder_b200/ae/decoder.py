@@ -82,6 +82,11 @@ class Decoder(_DeviceModule):
     @staticmethod
     def loss_device(x_dev, target_dev, bootstrap_ratio, with_grad=False):
         """Bootstrapped L2 on device tensors -> (loss 0-d tensor, grad or None)."""
+        if target_dev.dtype == torch.uint8:          # the kernel reads float*: a uint8 target is the image / 255 (as the trainer's feed)
+            target_dev = target_dev.to(torch.float32) / 255.0
+        if x_dev.dtype != torch.float32 or target_dev.dtype != torch.float32 or x_dev.shape != target_dev.shape:
+            raise ValueError("bootstrapped L2 wants float32 tensors of one shape, got %s %s / %s %s"
+                             % (x_dev.dtype, tuple(x_dev.shape), target_dev.dtype, tuple(target_dev.shape)))
         B = x_dev.shape[0]
         numel = x_dev[0].numel()
         loss = torch.empty((1,), dtype=torch.float32, device=x_dev.device)

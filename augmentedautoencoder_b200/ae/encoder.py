@@ -56,18 +56,25 @@ class _DeviceModule:
     def variable_names(self):
         return [n for kn, _, bn, _ in self._var_shapes for n in (kn, bn)]
 
-    def load_weights(self, weights):
-        """weights: {variable name (full scoped name, or without the scope prefix): array in the reference layout}."""
+    def load_weights(self, weights, strict=True):
+        """weights: {variable name (full scoped name, or without the scope prefix): array in the reference layout}.
+        Like ``tf.train.Saver.restore``, a variable of this module that the dict does not hold is an error (KeyError naming every
+        missing one; nothing is modified then) unless ``strict=False`` (partial update)."""
+        found, missing = {}, []
         for kn, ks, bn, bs in self._var_shapes:
             for name, shape in ((kn, ks), (bn, bs)):
                 short = "/".join(name.split("/")[-2:])
                 src = weights.get(name, weights.get(short))
                 if src is None:
+                    missing.append(name)
                     continue
                 arr = np.ascontiguousarray(np.asarray(src, dtype=np.float32))
                 if arr.shape != tuple(shape):
                     raise ValueError("%s: shape %s != expected %s" % (name, arr.shape, tuple(shape)))
-                self._host[name] = arr
+                found[name] = arr
+        if missing and strict:
+            raise KeyError("variables not found in the checkpoint / weight dict (wrong experiment scope?): %s" % ", ".join(missing))
+        self._host.update(found)
         for dev, h in self._handles.items():
             self._upload(dev, h)
 

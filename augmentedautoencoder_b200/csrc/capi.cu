@@ -158,6 +158,11 @@ struct aae_encoder {
   TcEncoder* tc = nullptr;  // tensor-core execution plan (AAE_PREC_TC_SPLIT)
   int last_batch = 0;
   bool last_was_tc = false;
+  // the fp32 tensors above are the master copy; the tensor-core plan holds packed (hi, lo) fp16 operands derived from them.
+  // w_version counts changes of the master copy (set_weights, Adam); tc_stale = the plan's operands are older than the masters
+  // (set by the optimizer step, which updates the masters in place; cleared by the lazy repack in the forward entry points).
+  uint64_t w_version = 1;
+  bool tc_stale = false;
   StageTimer timer;
 };
 
@@ -171,6 +176,8 @@ struct aae_decoder {
   DevBuf partials;
   TcDecoder* tc = nullptr;      // tensor-core execution plan (AAE_PREC_TC_SPLIT, forward only)
   int last_batch = 0;
+  uint64_t w_version = 1;       // see aae_encoder
+  bool tc_stale = false;
 };
 
 struct aae_codebook {
@@ -208,6 +215,7 @@ struct aae_trainer {
   DevBuf sample_sums, z, dz, rec;
   DevBuf dwm;           // gradient wrt merged sub-pixel weights
   TcTrainPlan* tc = nullptr;  // tensor-core backward plan (encoder and decoder created with AAE_PREC_TC_SPLIT)
+  uint64_t packed_enc_version = 0, packed_dec_version = 0;   // master-weight versions the plan's dgrad operands were packed from
 };
 
 // ============================================================================ misc
@@ -313,6 +321,7 @@ extern "C" int aae_encoder_set_weights(aae_encoder* h, int layer, const float* k
   DevBuf& b = layer < (int)h->conv.size() ? h->conv[layer].b : h->dense_b;
   if (kernel_any) AAE_TRY(copy_any(w.p, kernel_any, w.n * sizeof(float), s));
   if (bias_any) AAE_TRY(copy_any(b.p, bias_any, b.n * sizeof(float), s));
+  h->w_version += 1;
   if (h->tc && kernel_any) AAE_TRY(tc_encoder_pack_weights(h->tc, layer, w.p, s));
   if (h->tc) AAE_TRY(tc_encoder_set_bias(h->tc, layer, b.p));
   AAE_CUDA_OK(cudaStreamSynchronize(s));  // host source buffers may be freed by the caller on return
@@ -329,6 +338,17 @@ extern "C" int aae_encoder_get_weights(aae_encoder* h, int layer, float* kernel_
   if (kernel_any) AAE_TRY(copy_any(kernel_any, w.p, w.n * sizeof(float), s));
   if (bias_any) AAE_TRY(copy_any(bias_any, b.p, b.n * sizeof(float), s));
   AAE_CUDA_OK(cudaStreamSynchronize(s));
+  return AAE_OK;
+}
+
+// Re-derive the tensor-core plan's packed operands from the fp32 master weights after an optimizer step changed them in place
+// (inference in the training process -- Codebook.update_embedding, decoder.x -- must see the weights get_weights() returns).
+static int encoder_sync_tc(aae_encoder* h, cudaStream_t s) {
+  if (!h->tc || !h->tc_stale) return AAE_OK;
+  const int nl = (int)h->conv.size();
+  for (int i = 0; i < nl; ++i) AAE_TRY(tc_encoder_pack_weights(h->tc, i, h->conv[i].w.p, s));
+  AAE_TRY(tc_encoder_pack_weights(h->tc, nl, h->dense_w.p, s));
+  h->tc_stale = false;
   return AAE_OK;
 }
 
@@ -358,6 +378,7 @@ static int encoder_forward(aae_encoder* h, const void* crops, int src_u8, int B,
   h->last_batch = B;
   if (h->tc) {
     h->last_was_tc = true;
+    AAE_TRY(encoder_sync_tc(h, (cudaStream_t)stream));
     return tc_encoder_forward(h->tc, crops, src_u8, B, h->conv[0].w.p, h->conv[0].b.p, h->dense_b.p, z_out, (cudaStream_t)stream);
   }
   h->last_was_tc = false;
@@ -597,6 +618,7 @@ extern "C" int aae_decoder_set_weights(aae_decoder* h, int layer, const float* k
   if (kernel_any) AAE_TRY(copy_any(w.p, kernel_any, w.n * sizeof(float), s));
   if (bias_any) AAE_TRY(copy_any(b.p, bias_any, b.n * sizeof(float), s));
   if (layer > 0) h->conv[layer - 1].wm_dirty = true;
+  h->w_version += 1;
   if (h->tc) AAE_TRY(tc_decoder_pack_weights(h->tc, layer, kernel_any ? w.p : nullptr, bias_any ? b.p : nullptr, s));
   AAE_CUDA_OK(cudaStreamSynchronize(s));
   return AAE_OK;
@@ -612,6 +634,14 @@ extern "C" int aae_decoder_get_weights(aae_decoder* h, int layer, float* kernel_
   if (kernel_any) AAE_TRY(copy_any(kernel_any, w.p, w.n * sizeof(float), s));
   if (bias_any) AAE_TRY(copy_any(bias_any, b.p, b.n * sizeof(float), s));
   AAE_CUDA_OK(cudaStreamSynchronize(s));
+  return AAE_OK;
+}
+
+static int decoder_sync_tc(aae_decoder* h, cudaStream_t s) {   // see encoder_sync_tc
+  if (!h->tc || !h->tc_stale) return AAE_OK;
+  AAE_TRY(tc_decoder_pack_weights(h->tc, 0, h->dense_w.p, h->dense_b.p, s));
+  for (int l = 1; l <= (int)h->conv.size(); ++l) AAE_TRY(tc_decoder_pack_weights(h->tc, l, h->conv[l - 1].w.p, h->conv[l - 1].b.p, s));
+  h->tc_stale = false;
   return AAE_OK;
 }
 
@@ -657,7 +687,10 @@ extern "C" int aae_decoder_forward(aae_decoder* h, const float* z_dev, int batch
   AAE_REQUIRE(batch >= 1 && batch <= h->cfg.max_batch, "batch %d outside [1, max_batch=%d]", batch, h->cfg.max_batch);
   DeviceGuard g(h->device);
   h->last_batch = batch;
-  if (h->tc) return tc_decoder_forward(h->tc, z_dev, batch, x_out_dev, (cudaStream_t)stream);
+  if (h->tc) {
+    AAE_TRY(decoder_sync_tc(h, (cudaStream_t)stream));
+    return tc_decoder_forward(h->tc, z_dev, batch, x_out_dev, (cudaStream_t)stream);
+  }
   return decoder_forward_impl(h, z_dev, batch, x_out_dev, (cudaStream_t)stream);
 }
 
@@ -825,15 +858,22 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
   const int nl = (int)E->conv.size(), nd = (int)D->conv.size();
   const int n_units = tc_train_num_units(P), n_dec = tc_train_num_decoder_units(P);
   AAE_REQUIRE(n_dec == nd && n_units == nd + nl - 1, "tensor-core trainer: plan does not match the network");
-  // ---- operands follow the fp32 master weights (Adam updates those) ----
-  for (int i = 0; i < nl; ++i) AAE_TRY(tc_encoder_pack_weights(E->tc, i, E->conv[i].w.p, s));
-  AAE_TRY(tc_encoder_pack_weights(E->tc, nl, E->dense_w.p, s));
-  AAE_TRY(tc_decoder_pack_weights(D->tc, 0, D->dense_w.p, D->dense_b.p, s));
-  for (int l = 1; l <= nd; ++l) {   // forward and dgrad operands of a decoder layer share one merge of its 5x5 taps
-    AAE_TRY(tc_decoder_pack_weights(D->tc, l, D->conv[l - 1].w.p, D->conv[l - 1].b.p, s));
-    AAE_TRY(tc_train_pack_weights_merged(P, nd - l, tc_decoder_merged_weights(D->tc), s));
+  // ---- operands follow the fp32 master weights (Adam and set_weights change those) ----
+  AAE_TRY(encoder_sync_tc(E, s));
+  if (h->packed_dec_version != D->w_version || D->tc_stale) {
+    // forward and dgrad operands of a decoder layer share one merge of its 5x5 taps
+    AAE_TRY(tc_decoder_pack_weights(D->tc, 0, D->dense_w.p, D->dense_b.p, s));
+    for (int l = 1; l <= nd; ++l) {
+      AAE_TRY(tc_decoder_pack_weights(D->tc, l, D->conv[l - 1].w.p, D->conv[l - 1].b.p, s));
+      AAE_TRY(tc_train_pack_weights_merged(P, nd - l, tc_decoder_merged_weights(D->tc), s));
+    }
+    D->tc_stale = false;
+    h->packed_dec_version = D->w_version;
   }
-  for (int u = n_dec; u < n_units; ++u) AAE_TRY(tc_train_pack_weights(P, u, E->conv[nl - 1 - (u - n_dec)].w.p, s));
+  if (h->packed_enc_version != E->w_version) {
+    for (int u = n_dec; u < n_units; ++u) AAE_TRY(tc_train_pack_weights(P, u, E->conv[nl - 1 - (u - n_dec)].w.p, s));
+    h->packed_enc_version = E->w_version;
+  }
   AAE_TRY(tc_train_begin_step(P, s));
   // ---- forward ----
   E->last_batch = B; E->last_was_tc = true;
@@ -988,6 +1028,10 @@ extern "C" int aae_train_step(aae_trainer* h, const float* x_dev, const float* y
     }
   if (ab.count) AAE_TRY(launch_adam_multi(ab, lr_t, h->b1, h->b2, h->eps, s));
   for (auto& L : h->dec->conv) L.wm_dirty = true;   // the merged sub-pixel weights follow the updated taps
+  // the masters changed in place: every packed copy (inference plans, trainer dgrad operands) is now one step behind
+  h->enc->w_version += 1; h->dec->w_version += 1;
+  h->enc->tc_stale = h->enc->tc != nullptr;
+  h->dec->tc_stale = h->dec->tc != nullptr;
   return AAE_OK;
 }
 

@@ -205,3 +205,34 @@ def test_tc_training_steps_track_the_fp32_trainer(sess):
         del enc, dec, top
     assert traj[1][-1] < traj[1][0]
     assert np.max(np.abs(np.array(traj[0]) - np.array(traj[1]))) < 2e-4, traj
+
+
+def test_inference_after_a_training_step_uses_the_updated_weights(sess):
+    """Adam updates the fp32 master weights in place; the tensor-core plans keep packed (hi, lo) copies.  In-process inference
+    after training (Codebook.update_embedding, decoder.x: ae_embed.py:84-91 run after ae_train.py) must use the step-N
+    weights that get_weights() / the checkpoint hold -- i.e. equal a fresh handle loaded from get_weights()."""
+    from augmentedautoencoder_b200.ae.decoder import Decoder
+    from augmentedautoencoder_b200.ae.encoder import Encoder
+    from augmentedautoencoder_b200.ae.session import placeholder
+    enc, dec, top, ep, dp = _train_pair(1, 4)
+    xb = torch.from_numpy(np.random.RandomState(11).rand(3, 128, 128, 3).astype(np.float32)).cuda()
+    yb = torch.from_numpy(np.random.RandomState(12).rand(3, 128, 128, 3).astype(np.float32)).cuda()
+    z_before = enc.encode_device(xb).clone()
+    for _ in range(2):
+        top.step_device(xb, yb, update=True)
+    z_after = enc.encode_device(xb).clone()
+    rec_after = dec.decode_device(z_after).clone()
+    assert float((z_after - z_before).abs().max()) > 1e-4           # the step did move the weights
+    enc2 = Encoder(placeholder(np.float32, [None, 128, 128, 3]), 128, list(O.NUM_FILTER), 5, list(O.STRIDES), False, max_batch=4, precision=1)
+    dec2 = Decoder(placeholder(np.float32, [None, 128, 128, 3]), enc2.z, list(reversed(O.NUM_FILTER)), 5, list(reversed(O.STRIDES)), "L2", 4,
+                   False, False, max_batch=4, precision=1)
+    enc2.load_weights(enc.get_weights())
+    dec2.load_weights(dec.get_weights())
+    z_fresh = enc2.encode_device(xb)
+    assert torch.equal(z_after, z_fresh), float((z_after - z_fresh).abs().max())
+    assert torch.equal(rec_after, dec2.decode_device(z_fresh))
+    # ... and training continues from the same state after the inference calls (the trainer's operands follow too)
+    l3 = float(top.step_device(xb, yb, update=True))
+    enc3, dec3, top3, _, _ = _train_pair(1, 4)
+    ref = [float(top3.step_device(xb, yb, update=True)) for _ in range(3)]
+    assert abs(l3 - ref[2]) < 1e-6, (l3, ref)

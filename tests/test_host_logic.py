@@ -77,10 +77,13 @@ def test_variable_scope_names_follow_the_reference():
     assert np.all(w["obj_05/conv2d/bias"] == 0)                      # tf.layers default: zero bias, glorot-uniform kernel
     lim = np.sqrt(6.0 / (25 * 3 + 25 * 128))
     assert np.abs(w["obj_05/conv2d/kernel"]).max() <= lim
-    enc.load_weights({"conv2d_3/bias": np.ones(512, np.float32)})   # short names are accepted
+    with pytest.raises(KeyError, match="obj_05/dense/kernel"):      # like tf.train.Saver.restore: a missing variable is an error
+        enc.load_weights({"conv2d_3/bias": np.ones(512, np.float32)})
+    assert np.all(enc.get_weights()["obj_05/conv2d_3/bias"] == 0)   # ... and nothing was modified
+    enc.load_weights({"conv2d_3/bias": np.ones(512, np.float32)}, strict=False)   # partial update; short names are accepted
     assert np.all(enc.get_weights()["obj_05/conv2d_3/bias"] == 1)
     with pytest.raises(ValueError):
-        enc.load_weights({"dense/kernel": np.zeros((3, 3), np.float32)})
+        enc.load_weights({"dense/kernel": np.zeros((3, 3), np.float32)}, strict=False)
     with pytest.raises(NotImplementedError):
         Encoder(x, 128, [128], 5, [2], True)
 
@@ -113,6 +116,51 @@ def test_saver_round_trip(tmp_path):
     assert np.array_equal(cb2.embedding_normalized.value(), E)
     with pytest.raises(FileNotFoundError):
         factory.restore_checkpoint(None, factory.Saver([enc2]), str(tmp_path / "nothing"))
+    # a checkpoint of another experiment scope must not restore "successfully" (tf.train.Saver raises NotFoundError)
+    with S.variable_scope("other_scope"):
+        enc3 = Encoder(S.placeholder(np.float32, [None, 32, 32, 3]), 16, [8, 16], 5, [2, 2], False, seed=3)
+        cb3 = Codebook(enc3, ds, True)
+    before = enc3.get_weights()["other_scope/conv2d/kernel"].copy()
+    with pytest.raises(KeyError, match="other_scope/embedding_normalized|other_scope/conv2d/kernel"):
+        factory.restore_checkpoint(None, factory.Saver([enc3, cb3]), str(tmp_path / "checkpoints"))
+    assert np.array_equal(enc3.get_weights()["other_scope/conv2d/kernel"], before)
+    with pytest.raises(KeyError, match="embedding_normalized"):     # encoder-only checkpoint into a codebook saver
+        p2 = factory.Saver([enc]).save(None, str(tmp_path / "enc_only" / "chkpt"), global_step=1)
+        factory.Saver([enc2, cb2]).restore(None, p2)
+    factory.Saver([enc2, cb2]).restore(None, p2, strict=False)
+
+
+def test_queue_pulls_one_fresh_batch_per_run():
+    """ae_train.py:128 `sess.run(train_op)` dequeues a new batch every run; x and y of one run belong to the same batch."""
+    import gc
+
+    import torch
+    from augmentedautoencoder_b200.ae import factory
+    from augmentedautoencoder_b200.ae.session import RunContext
+
+    class FakeSession:
+        device = torch.device("cpu")
+
+    class FakeDataset:
+        shape = (4, 4, 3)
+
+    pulls = []
+
+    def source(n):
+        i = len(pulls)
+        pulls.append(i)
+        return np.full((n, 4, 4, 3), i, np.float32), np.full((n, 4, 4, 3), -i, np.float32)
+
+    q = factory.Queue(FakeDataset(), 1, 1, 2, source=source)
+    seen = []
+    for _ in range(6):
+        ctx = RunContext(FakeSession(), {})              # what Session.run builds per call; freed (and its address reused) every time
+        x, y = ctx.get(q.x), ctx.get(q.y)
+        assert float(x[0, 0, 0, 0]) == -float(y[0, 0, 0, 0])     # same dequeue
+        seen.append(int(x[0, 0, 0, 0]))
+        del ctx
+        gc.collect()
+    assert seen == list(range(6)) and len(pulls) == 6
 
 
 def test_tf_tensor_bundle_round_trip(tmp_path):
