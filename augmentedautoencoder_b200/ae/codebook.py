@@ -247,6 +247,52 @@ class PendingIndices:
         return self._host.numpy().astype(np.int64)[:, 0]   # astype copies: the pinned buffer goes back to the ring
 
 
+def _sq_scalar(a):
+    """x**2 exactly as the reference evaluates it: on numpy float64 SCALARS (``t_est[2]**2``, codebook.py:121), which goes
+    through C pow() and is not always bit-identical to the array fast path x*x."""
+    flat = np.asarray(a, dtype=np.float64).ravel()
+    return np.array([v ** 2 for v in flat], dtype=np.float64).reshape(np.shape(a))
+
+
+def lift_pose_batch(idcs, rs_table, embed_obj_bbs, predicted_bbs, K_test, K_train, render_radius, depth_pred=None):
+    """``auto_pose6d``'s numpy tail (auto_pose/ae/codebook.py:82-129) for ALL detections of one object class at once:
+    idcs [D, k] codebook rows (k hypotheses per detection), predicted_bbs [D, 4] xywh -> (Rs [D, k, 3, 3], ts [D, k, 3]),
+    float64, bit-identical to calling the reference per detection (same operations on the same dtypes in the same order;
+    tests/test_host_logic.py checks it against the reference-generated golden and against the per-detection loop)."""
+    idcs = np.asarray(idcs)
+    if idcs.ndim == 1:
+        idcs = idcs[:, None]
+    D, k = idcs.shape
+    pb = np.asarray(predicted_bbs).reshape(D, 4)
+    R = rs_table[idcs]                                           # [D, k, 3, 3]
+    rb = np.asarray(embed_obj_bbs)[idcs]                         # [D, k, 4] rendered bounding boxes
+    K_diag_ratio = np.sqrt(K_test[0, 0] ** 2 + K_test[1, 1] ** 2) / np.sqrt(K_train[0, 0] ** 2 + K_train[1, 1] ** 2)
+    if depth_pred is None:
+        r32, p32 = np.float32(rb[..., 2:]), np.float32(pb[:, 2:])
+        # np.linalg.norm of a 2-vector of float32 = sqrt(x . x) evaluated in float32
+        n_r = np.sqrt(r32[..., 0] * r32[..., 0] + r32[..., 1] * r32[..., 1])
+        n_p = np.sqrt(p32[:, 0] * p32[:, 0] + p32[:, 1] * p32[:, 1])
+        z = (n_r / n_p[:, None]) * K_diag_ratio * render_radius
+    else:
+        z = np.broadcast_to(np.asarray(depth_pred, dtype=np.float64).reshape(-1, 1), (D, k)).copy()
+    cx_train = rb[..., 0] + rb[..., 2] / 2. - K_train[0, 2]
+    cy_train = rb[..., 1] + rb[..., 3] / 2. - K_train[1, 2]
+    cx_test = (pb[:, 0] + pb[:, 2] / 2 - K_test[0, 2])[:, None]
+    cy_test = (pb[:, 1] + pb[:, 3] / 2 - K_test[1, 2])[:, None]
+    tx = cx_test * z / K_test[0, 0] - cx_train * render_radius / K_train[0, 0]
+    ty = cy_test * z / K_test[1, 1] - cy_train * render_radius / K_train[1, 1]
+    z = z.astype(np.float64)
+    ts = np.stack([tx, ty, z], axis=-1).astype(np.float64)
+    ay = np.arctan(ts[..., 0] / np.sqrt(_sq_scalar(ts[..., 2]) + _sq_scalar(ts[..., 1])))
+    ax = -np.arctan(ts[..., 1] / ts[..., 2])
+    cax, sax, cay, say = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay)
+    Rx = np.zeros((D, k, 3, 3))
+    Rx[..., 0, 0], Rx[..., 1, 1], Rx[..., 1, 2], Rx[..., 2, 1], Rx[..., 2, 2] = 1, cax, -sax, sax, cax
+    Ry = np.zeros((D, k, 3, 3))
+    Ry[..., 0, 0], Ry[..., 0, 2], Ry[..., 1, 1], Ry[..., 2, 0], Ry[..., 2, 2] = cay, say, 1, -say, cay
+    return np.matmul(Ry, np.matmul(Rx, R)), ts
+
+
 def lift_pose(idcs, rs_table, embed_obj_bbs, predicted_bb, K_test, K_train, render_radius, depth_pred=None):
     """The numpy tail of Codebook.auto_pose6d (codebook.py:82-129): depth from the ratio of rendered to detected bbox
     diagonals scaled by the focal-length ratio, lateral offset from the bbox centres, and the rotation that keeps the

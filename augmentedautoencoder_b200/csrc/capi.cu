@@ -516,7 +516,16 @@ extern "C" int aae_topk_merge(const float* scores_dev, const int32_t* idx_dev, i
                               float* scores_out_dev, int32_t* idx_out_dev, void* stream) {
   AAE_REQUIRE(scores_dev && idx_dev && scores_out_dev && idx_out_dev, "null argument");
   AAE_REQUIRE(batch >= 1 && k >= 1, "bad batch/k");
-  return launch_topk_merge(scores_dev, idx_dev, n_shards, batch, k, scores_out_dev, idx_out_dev, (cudaStream_t)stream);
+  return launch_topk_merge(scores_dev, idx_dev, (long long)batch * k, n_shards, batch, k, scores_out_dev, idx_out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int aae_topk_merge_packed(const void* packed_dev, int n_shards, int batch, int k, float* scores_out_dev, int32_t* idx_out_dev,
+                                     void* stream) {
+  AAE_REQUIRE(packed_dev && scores_out_dev && idx_out_dev, "null argument");
+  AAE_REQUIRE(batch >= 1 && k >= 1, "bad batch/k");
+  const float* s0 = (const float*)packed_dev;
+  const int32_t* i0 = (const int32_t*)packed_dev + (size_t)batch * k;
+  return launch_topk_merge(s0, i0, 2ll * batch * k, n_shards, batch, k, scores_out_dev, idx_out_dev, (cudaStream_t)stream);
 }
 
 // ============================================================================ training input pipeline

@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(1024) topk_from_cos_kernel(const float* __rest
 }
 
 // in: [S, B, k] sorted lists -> out: [B, k]; one thread per query, k-way head merge.
-__global__ void topk_merge_kernel(const float* __restrict__ s_in, const int* __restrict__ i_in, int S, int B, int k,
+// shard_stride = elements between consecutive shards' lists (B*k when contiguous; 2*B*k for the packed [S][2][B][k] exchange buffer)
+__global__ void topk_merge_kernel(const float* __restrict__ s_in, const int* __restrict__ i_in, long long shard_stride, int S, int B, int k,
                                   float* __restrict__ s_out, int* __restrict__ i_out) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= B) return;
@@ -172,7 +173,7 @@ __global__ void topk_merge_kernel(const float* __restrict__ s_in, const int* __r
     int bi = INT_MAX, bsh = -1;
     for (int s = 0; s < S; ++s) {
       if (head[s] >= k) continue;
-      const long long o = ((long long)s * B + q) * k + head[s];
+      const long long o = (long long)s * shard_stride + (long long)q * k + head[s];
       const int idx = i_in[o];
       if (idx < 0) continue;  // exhausted shard list
       if (better(s_in[o], idx, bs, bi)) { bs = s_in[o]; bi = idx; bsh = s; }
@@ -210,9 +211,10 @@ int launch_topk_from_cos(const float* cos, long long n_rows, int B, long long ro
   return AAE_OK;
 }
 
-int launch_topk_merge(const float* s_in, const int* i_in, int S, int B, int k, float* s_out, int* i_out, cudaStream_t stream) {
+int launch_topk_merge(const float* s_in, const int* i_in, long long shard_stride, int S, int B, int k, float* s_out, int* i_out,
+                      cudaStream_t stream) {
   AAE_REQUIRE(S >= 1 && S <= 64, "topk_merge: n_shards=%d must be in [1,64]", S);
-  topk_merge_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, stream>>>(s_in, i_in, S, B, k, s_out, i_out);
+  topk_merge_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, stream>>>(s_in, i_in, shard_stride, S, B, k, s_out, i_out);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }

@@ -15,7 +15,7 @@ import torch
 
 from .. import _lib
 from ..ae import factory, utils
-from ..ae.codebook import lift_pose
+from ..ae.codebook import lift_pose, lift_pose_batch
 from ..ae.session import Session
 from .m3_interfaces import PoseEstimate, PoseEstInterface
 
@@ -135,12 +135,13 @@ class AePoseEstimator(PoseEstInterface):
             radius = train_args.getfloat('Dataset', 'RADIUS')
             if cb.embed_obj_bbs_values is None:
                 cb.embed_obj_bbs_values = sess.run(cb.embed_obj_bbs_var)
-            for (o, box_xywh), i in zip(items, idcs):
-                Rs, ts = lift_pose(np.array([i]), cb._dataset.viewsphere_for_embedding, cb.embed_obj_bbs_values, box_xywh,
-                                   np.asarray(camK), K_train, radius)
+            # pose lift of all detections of this class in one vectorised call (codebook.py:82-129)
+            Rs, ts = lift_pose_batch(idcs[:, None], cb._dataset.viewsphere_for_embedding, cb.embed_obj_bbs_values,
+                                     np.array([it[1] for it in items]), np.asarray(camK), K_train, radius)
+            for j, (o, _) in enumerate(items):
                 H_est = np.eye(4)
-                H_est[:3, :3] = Rs.squeeze()
-                H_est[:3, 3] = ts.squeeze() if mm else ts.squeeze() / 1000.
+                H_est[:3, :3] = Rs[j, 0]
+                H_est[:3, 3] = ts[j, 0] if mm else ts[j, 0] / 1000.
                 if self._camPose:
                     H_est = np.dot(camPose, H_est)
                 results[o] = PoseEstimate(name=clas, trafo=H_est)

@@ -97,45 +97,52 @@ class ShardedCodebook:
             _lib.check(st, "sharded codebook create")
         self._handle = h
 
-    def _local_match(self, z, k, upright):
-        """z [B, J] on self.device -> (scores [B, k], global idx [B, k]); an empty shard returns (-inf, -1)."""
+    def _local_match(self, z, k, upright, s_out, i_out):
+        """z [B, J] on self.device -> this shard's top-k written into s_out [B, k] float32 / i_out [B, k] int32 (global row
+        indices); list positions past the shard's size, and every position of an empty shard, hold (-inf, -1)."""
         B = z.shape[0]
-        scores = torch.full((B, k), float("-inf"), dtype=torch.float32, device=z.device)
-        idx = torch.full((B, k), -1, dtype=torch.int32, device=z.device)
-        if self._handle is None:
-            return scores, idx
-        kk = min(k, self.hi - self.lo)
-        s_loc = torch.empty((B, kk), dtype=torch.float32, device=z.device)
-        i_loc = torch.empty((B, kk), dtype=torch.int32, device=z.device)
+        kk = min(k, self.hi - self.lo) if self._handle is not None else 0
+        if kk < k:
+            s_out.fill_(float("-inf"))
+            i_out.fill_(-1)
+            if kk == 0:
+                return
+        direct = kk == k and s_out.is_contiguous() and i_out.is_contiguous()
+        s_loc = s_out if direct else torch.empty((B, kk), dtype=torch.float32, device=z.device)
+        i_loc = i_out if direct else torch.empty((B, kk), dtype=torch.int32, device=z.device)
         stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
         for a in range(0, B, self.max_batch):
             e = min(B, a + self.max_batch)
             _lib.check(_lib.lib().aae_codebook_match(self._handle, _lib.ptr(z[a:e]), e - a, kk, int(bool(upright)), _lib.ptr(s_loc[a:e]),
                                                      _lib.ptr(i_loc[a:e]), stream), "sharded match")
-        scores[:, :kk], idx[:, :kk] = s_loc, i_loc
-        return scores, idx
+        if not direct:
+            s_out[:, :kk], i_out[:, :kk] = s_loc, i_loc
 
-    def _merge(self, all_scores, all_idx):
-        """[W, B, k] gathered lists -> [B, k]: score descending, ties to the lowest global index (aae_topk_merge)."""
-        W, B, k = all_scores.shape
-        so = torch.empty((B, k), dtype=torch.float32, device=all_scores.device)
-        io = torch.empty((B, k), dtype=torch.int32, device=all_scores.device)
-        _lib.check(_lib.lib().aae_topk_merge(_lib.ptr(all_scores), _lib.ptr(all_idx), W, B, k, _lib.ptr(so), _lib.ptr(io),
-                                             C.c_void_p(torch.cuda.current_stream(all_scores.device).cuda_stream)), "topk merge")
+    def _merge(self, packed):
+        """[W, 2, B, k] gathered exchange buffers (plane 0 = float32 score bits, plane 1 = int32 global indices) -> [B, k]:
+        score descending, ties to the lowest global index (aae_topk_merge_packed)."""
+        W, _, B, k = packed.shape
+        so = torch.empty((B, k), dtype=torch.float32, device=packed.device)
+        io = torch.empty((B, k), dtype=torch.int32, device=packed.device)
+        _lib.check(_lib.lib().aae_topk_merge_packed(_lib.ptr(packed), W, B, k, _lib.ptr(so), _lib.ptr(io),
+                                                    C.c_void_p(torch.cuda.current_stream(packed.device).cuda_stream)), "topk merge")
         return so, io
 
     # -- the exchange step -------------------------------------------------------------------------------------------
     def match(self, z, k=1, upright=False):
-        """Every rank passes the same queries z [B, J]; every rank gets the global (scores [B,k], idx [B,k])."""
-        s, i = self._local_match(z.contiguous(), k, upright)
+        """Every rank passes the same queries z [B, J]; every rank gets the global (scores [B,k], idx [B,k]).
+        ONE collective: the shard's scores and indices are produced side by side in one [2, B, k] buffer (8 bytes per entry)
+        and all-gathered together -- the exchange is pure latency, so one NCCL call instead of two halves its cost."""
+        z = z.contiguous()
+        B = z.shape[0]
+        pk = torch.empty((2, B, k), dtype=torch.int32, device=z.device)
+        s, i = pk[0].view(torch.float32), pk[1]
+        self._local_match(z, k, upright, s, i)
         if self.world == 1:
             return s, i
-        B = s.shape[0]
-        all_s = torch.empty((self.world * B, k), dtype=s.dtype, device=s.device)   # rank-major concatenation = [W, B, k]
-        all_i = torch.empty((self.world * B, k), dtype=i.dtype, device=i.device)
-        dist.all_gather_into_tensor(all_s, s.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(all_i, i.contiguous(), group=self.group)
-        return self._merge(all_s.view(self.world, B, k), all_i.view(self.world, B, k))
+        allpk = torch.empty((self.world * 2, B, k), dtype=torch.int32, device=z.device)     # rank-major concatenation = [W, 2, B, k]
+        dist.all_gather_into_tensor(allpk, pk, group=self.group)
+        return self._merge(allpk.view(self.world, 2, B, k))
 
     def match_split_queries(self, z_local, batch_total, k=1, upright=False):
         """Encoder work split across ranks: each rank encoded only its ``split_batch`` slice; the latents ([B_r, J],
@@ -143,11 +150,14 @@ class ShardedCodebook:
         if self.world == 1:
             return self.match(z_local, k, upright)
         per = -(-batch_total // self.world)
-        pad = torch.zeros((per, z_local.shape[1]), dtype=z_local.dtype, device=z_local.device)
-        pad[:z_local.shape[0]] = z_local
+        if z_local.shape[0] == per:
+            pad = z_local.contiguous()
+        else:
+            pad = torch.zeros((per, z_local.shape[1]), dtype=z_local.dtype, device=z_local.device)
+            pad[:z_local.shape[0]] = z_local
         all_z = torch.empty((self.world * per, z_local.shape[1]), dtype=z_local.dtype, device=z_local.device)
         dist.all_gather_into_tensor(all_z, pad, group=self.group)
-        return self.match(all_z[:batch_total].contiguous(), k, upright)
+        return self.match(all_z[:batch_total], k, upright)
 
     def close(self):
         if self._handle is not None:
@@ -163,9 +173,11 @@ class ShardedCodebook:
 
 # --------------------------------------------------------------------------------------------------------- object routing
 class ObjectRouter:
-    """One (encoder, codebook) pair per object class, classes spread over the ranks (BASELINE config 4).  Every rank sees
-    the same mixed batch of crops and class ids; it runs the crops of the classes it owns, and the per-crop results are
-    combined with a MAX all-reduce (every position is written by exactly one rank, all others hold the identity)."""
+    """One (encoder, codebook) pair per object class, classes spread over the ranks (BASELINE config 4; the reference's
+    registry is AePoseEstimator.all_codebooks, auto_pose/m3_interface/ae_pose_estimator.py:48-78, used per detection at
+    :143-170).  Every rank sees the class ids of the mixed batch; a rank touches -- and, with ``route_host``, uploads -- only
+    the crops of the classes it owns.  The per-crop results are combined by ONE all-reduce: every position is written by
+    exactly one rank and is zero everywhere else, so an integer SUM over [2, B] (float32 score bits, index + 1) is exact."""
 
     def __init__(self, codebooks_by_class, all_class_ids, group=None):
         """codebooks_by_class: {class id: Codebook} for the classes THIS rank owns (see ``owner_of_class``)."""
@@ -173,31 +185,67 @@ class ObjectRouter:
         self.rank, self.world = _world(group)
         self.owner = owner_of_class(all_class_ids, self.world)
         self.codebooks = dict(codebooks_by_class)
-        missing = [c for c, r in self.owner.items() if r == self.rank and c not in self.codebooks]
+        self.mine = sorted(c for c, r in self.owner.items() if r == self.rank)
+        missing = [c for c in self.mine if c not in self.codebooks]
         if missing:
             raise ValueError("rank %d owns classes %s but has no codebook for them" % (self.rank, missing))
+        self._stage = None
 
     def _run_class(self, cls, crops_dev):
         return self.codebooks[cls].nearest_idx_device(crops_dev, k=1)
 
-    def route(self, crops_dev, class_ids):
-        """crops_dev [B,H,W,C] on this rank's device, class_ids: length-B sequence.  Returns (scores [B], idx [B]) complete on
-        every rank; crops of unknown classes get (-inf, -1) (the reference skips them, ae_pose_estimator.py:147-149)."""
+    def plan(self, class_ids):
+        """Host-side routing table of one mixed batch: [(class, positions in the batch)] for the classes this rank owns."""
         class_ids = np.asarray(class_ids)
-        B = len(class_ids)
-        scores = torch.full((B,), float("-inf"), dtype=torch.float32, device=crops_dev.device)
-        idx = torch.full((B,), -1, dtype=torch.int32, device=crops_dev.device)
-        for cls, owner in self.owner.items():
-            if owner != self.rank:
-                continue
+        out = []
+        for cls in self.mine:
             sel = np.nonzero(class_ids == cls)[0]
-            if len(sel) == 0:
-                continue
-            sel_t = torch.from_numpy(sel).to(crops_dev.device)
-            s, i = self._run_class(cls, crops_dev.index_select(0, sel_t).contiguous())
-            scores[sel_t] = s[:, 0]
-            idx[sel_t] = i[:, 0]
+            if len(sel):
+                out.append((cls, sel))
+        return out
+
+    def _exchange(self, B, parts, device):
+        """parts: [(positions int64 tensor on `device`, scores [n, 1], idx [n, 1])] of this rank -> complete (scores [B], idx [B])
+        on every rank; positions nobody owns (unknown class: the reference skips those detections, ae_pose_estimator.py:147-149)
+        come back as (-inf, -1)."""
+        pk = torch.zeros((2, B), dtype=torch.int32, device=device)
+        for pos, s, i in parts:
+            pk[0, pos] = s[:, 0].contiguous().view(torch.int32)
+            pk[1, pos] = i[:, 0] + 1
         if self.world > 1:
-            dist.all_reduce(scores, op=dist.ReduceOp.MAX, group=self.group)
-            dist.all_reduce(idx, op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(pk, op=dist.ReduceOp.SUM, group=self.group)
+        idx = pk[1] - 1
+        scores = torch.where(idx >= 0, pk[0].view(torch.float32), torch.full((), float("-inf"), device=device))
         return scores, idx
+
+    def route(self, crops_dev, class_ids):
+        """crops_dev [B,H,W,C] already on this rank's device.  Returns (scores [B], idx [B]) complete on every rank."""
+        parts = []
+        for cls, sel in self.plan(class_ids):
+            pos = torch.from_numpy(sel).to(crops_dev.device)
+            s, i = self._run_class(cls, crops_dev.index_select(0, pos).contiguous())
+            parts.append((pos, s, i))
+        return self._exchange(len(class_ids), parts, crops_dev.device)
+
+    def route_host(self, crops_host, class_ids, device):
+        """crops_host: the mixed batch in HOST memory (torch uint8 tensor [B,H,W,C], ideally pinned).  This rank gathers the
+        crops of its own classes into a pinned staging buffer and uploads only those (1/world of the batch on average) --
+        not the whole batch on every rank.  Same return value as ``route``."""
+        plan = self.plan(class_ids)
+        n_own = sum(len(sel) for _, sel in plan)
+        parts = []
+        if n_own:
+            if self._stage is None or self._stage.shape[0] < n_own or self._stage.shape[1:] != crops_host.shape[1:]:
+                cap = max(n_own, -(-len(class_ids) // max(1, self.world)) * 2)
+                self._stage = torch.empty((cap,) + tuple(crops_host.shape[1:]), dtype=crops_host.dtype,
+                                          pin_memory=torch.cuda.is_available() and device.type == "cuda")
+            order = torch.from_numpy(np.concatenate([sel for _, sel in plan]))
+            torch.index_select(crops_host, 0, order, out=self._stage[:n_own])
+            own_dev = self._stage[:n_own].to(device, non_blocking=True)
+            pos_dev = order.to(device, non_blocking=True)
+            a = 0
+            for cls, sel in plan:
+                s, i = self._run_class(cls, own_dev[a:a + len(sel)])
+                parts.append((pos_dev[a:a + len(sel)], s, i))
+                a += len(sel)
+        return self._exchange(len(class_ids), parts, device)

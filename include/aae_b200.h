@@ -127,6 +127,12 @@ AAE_API int aae_codebook_cosine(aae_codebook* h, const float* z_dev, int batch, 
  * unsharded match. */
 AAE_API int aae_topk_merge(const float* scores_dev, const int32_t* idx_dev, int n_shards, int batch, int k,
                            float* scores_out_dev, int32_t* idx_out_dev, void* stream);
+/* Same merge for the single-collective exchange: every rank's match writes its scores and indices into ONE buffer
+ * [2][B][k] (plane 0 float32 scores, plane 1 int32 global indices -- 8 bytes per (query, k)), one NCCL all-gather
+ * concatenates them to packed_dev = [n_shards][2][B][k].  Halves the collective count of the row-sharded path, whose
+ * whole cost is collective latency (no reference counterpart: codebook.py:63-71 is single-device). */
+AAE_API int aae_topk_merge_packed(const void* packed_dev, int n_shards, int batch, int k,
+                                  float* scores_out_dev, int32_t* idx_out_dev, void* stream);
 AAE_API int64_t aae_codebook_rows(const aae_codebook* h);
 /* Same contract as aae_encoder_profile; one stage: the whole fused match (k = 1). */
 AAE_API int aae_codebook_profile(aae_codebook* h, int enable, float* stage_ms_out, int capacity);

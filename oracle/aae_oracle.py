@@ -526,3 +526,71 @@ def auto_pose6d_lift(idcs: np.ndarray, rs_table: np.ndarray, embed_obj_bbs: np.n
         r_corr_y = np.array([[np.cos(d_alpha_y), 0, np.sin(d_alpha_y)], [0, 1, 0], [-np.sin(d_alpha_y), 0, np.cos(d_alpha_y)]])
         rs_est[i] = np.dot(r_corr_y, np.dot(r_corr_x, rs_est[i]))
     return rs_est, ts_est
+
+
+# ----------------------------------------------------------------------------------------
+# The same inference data flow with the variables held resident, as a tf.Session holds them:
+# the timed CPU baseline (bench.py cpu_baseline / --impl reference).  Arithmetic = nearest_rotation_idcs.
+# ----------------------------------------------------------------------------------------
+class ResidentCpuPath:
+    """Codebook.nearest_rotation(x, return_idcs=True) on the CPU (auto_pose/ae/codebook.py:55-73 + encoder.py:37-68) with
+    every variable converted ONCE to the layout the convolution library wants (OIHW kernels in channels_last memory, the dense
+    kernel re-indexed from TF's NHWC flatten order to the NCHW order the activations are in, the codebook transposed) --
+    a fair CPU baseline must not re-wrap 59 MB of weights per call.  The full [B, N] cosine matrix is materialised and scanned
+    on the host, as the reference does."""
+
+    def __init__(self, enc_params: Dict[str, np.ndarray], codebook: np.ndarray, strides=STRIDES):
+        self.layers = []
+        i = 0
+        hw = None
+        while True:
+            name = "conv2d" if i == 0 else f"conv2d_{i}"
+            if f"{name}/kernel" not in enc_params or i >= len(strides):
+                break
+            k = torch.from_numpy(np.ascontiguousarray(enc_params[f"{name}/kernel"])).permute(3, 2, 0, 1)
+            k = k.contiguous(memory_format=torch.channels_last)
+            self.layers.append((k, torch.from_numpy(np.ascontiguousarray(enc_params[f"{name}/bias"])), int(strides[i])))
+            i += 1
+        cout = self.layers[-1][0].shape[0]
+        dk = enc_params["dense/kernel"]                       # rows in (h, w, c) order (tf.layers.flatten of NHWC)
+        hw = int(round(math.sqrt(dk.shape[0] // cout)))
+        self.dense_w = torch.from_numpy(np.ascontiguousarray(dk.reshape(hw, hw, cout, -1).transpose(2, 0, 1, 3).reshape(dk.shape[0], -1)))
+        self.dense_b = torch.from_numpy(np.ascontiguousarray(enc_params["dense/bias"]))
+        self.codebook_t = torch.from_numpy(np.ascontiguousarray(codebook.astype(np.float32).T))
+
+    def cos(self, crops: np.ndarray) -> np.ndarray:
+        x = torch.from_numpy(preprocess(crops)).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            for k, b, s in self.layers:
+                pt, pb = _same_pads(x.shape[2], k.shape[2], s)
+                pl, pr = _same_pads(x.shape[3], k.shape[3], s)
+                x = torch.relu(F.conv2d(F.pad(x, (pl, pr, pt, pb)), k, b, stride=s))
+            z = x.reshape(x.shape[0], -1) @ self.dense_w + self.dense_b     # NCHW flatten against the re-indexed kernel
+            ss = torch.clamp((z * z).sum(1, keepdim=True), min=1e-12)
+            zq = z * torch.rsqrt(ss)
+            return (zq @ self.codebook_t).numpy()
+
+    def __call__(self, crops: np.ndarray) -> np.ndarray:
+        return np.argmax(self.cos(crops), axis=1)
+
+
+def best_thread_count(fn, candidates=(1, 2, 4, 8, 16, 32, 64, 128, 256), repeats: int = 2):
+    """Times ``fn()`` under torch.set_num_threads(t) for every candidate t <= the machine's cores and leaves torch set to the
+    fastest.  Returns (threads, seconds per call at that setting, {t: seconds})."""
+    import os
+    import time
+    ncpu = os.cpu_count() or 1
+    cands = sorted({t for t in candidates if t <= ncpu} | {ncpu})
+    table = {}
+    for t in cands:
+        torch.set_num_threads(t)
+        fn()
+        best = float("inf")
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        table[t] = best
+    win = min(table, key=table.get)
+    torch.set_num_threads(win)
+    return win, table[win], table

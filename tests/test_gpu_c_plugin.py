@@ -25,10 +25,13 @@ def test_row_sharded_match_is_bit_identical_to_unsharded(sess, precision):
     rows = np.array([lo + 7 for lo, hi in spans] + [36 * 400 + 3, 35, n - 1])
     z = torch.from_numpy((E[rows] * 1.7).astype(np.float32)).cuda()
     k = 4 if precision == 0 else 1   # k > 1 is served by the exact fp32 kernels in both modes; compare like with like
-    per = [s._local_match(z, k, False) for s in shards]
-    all_s = torch.stack([p[0] for p in per]).contiguous()
-    all_i = torch.stack([p[1] for p in per]).contiguous()
-    s, i = shards[0]._merge(all_s, all_i)
+    def gather(kk, upright):
+        """What the NCCL all-gather of the per-rank [2, B, k] exchange buffers produces: [W, 2, B, k]."""
+        packed = torch.empty((W, 2, z.shape[0], kk), dtype=torch.int32, device=z.device)
+        for r, sh in enumerate(shards):
+            sh._local_match(z, kk, upright, packed[r, 0].view(torch.float32), packed[r, 1])
+        return packed
+    s, i = shards[0]._merge(gather(k, False))
     p = O.make_encoder_params(42)
     cb = _codebook(_enc(0, 64, p), E, max_batch=64, precision=precision)
     s_ref, i_ref = cb.match_device(z, k=1)
@@ -45,8 +48,7 @@ def test_row_sharded_match_is_bit_identical_to_unsharded(sess, precision):
         assert np.array_equal(i.cpu().numpy(), ik.cpu().numpy()) and np.array_equal(s.cpu().numpy(), sk.cpu().numpy())
     for b in range(len(rows)):
         assert np.max(np.abs(s.cpu().numpy()[b] - cos[b, i.cpu().numpy()[b]])) < 2e-6
-    su = [sh._local_match(z, 1, True) for sh in shards]
-    _, iu = shards[0]._merge(torch.stack([p_[0] for p_ in su]).contiguous(), torch.stack([p_[1] for p_ in su]).contiguous())
+    _, iu = shards[0]._merge(gather(1, True))
     assert np.array_equal(iu.cpu().numpy()[:, 0], O.select_indices(cos, upright=True, num_cyclo=36))
 
 

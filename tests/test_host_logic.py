@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from augmentedautoencoder_b200.ae import utils
-from augmentedautoencoder_b200.ae.codebook import lift_pose
+from augmentedautoencoder_b200.ae.codebook import lift_pose, lift_pose_batch
 from augmentedautoencoder_b200.ae.dataset import Dataset
 
 
@@ -23,6 +23,35 @@ def test_viewsphere_matches_reference(golden_dir):
     assert full.embedding_size == 92232
     assert np.array_equal(R[::36], ref["view_R"]) and np.array_equal(R[:72], ref["first_rows"])
     assert np.array_equal(R[-36:], ref["last_rows"]) and np.array_equal(R[ref["probe_idx"]], ref["probe_R"])
+
+
+def test_lift_pose_batch_is_bit_identical_to_the_per_detection_call(golden_dir):
+    """the vectorised pose lift used by AePoseEstimator.process == the reference's per-detection tail
+    (codebook.py:82-129), bit for bit, on the reference-generated golden and on 3000 random detections."""
+    p = g(golden_dir, "pose_lift.npz")
+    rs = Dataset(None, min_n_views=2562, num_cyclo=36, radius=700).viewsphere_for_embedding
+    for i in range(3):
+        idcs = np.atleast_1d(p[f"c{i}_idcs"])
+        table = np.zeros((92232, 4), dtype=np.int32)
+        table[idcs] = p[f"c{i}_bbs_at_idcs"]
+        r, t = lift_pose_batch(idcs[None, :], rs, table, np.asarray(p[f"c{i}_bb"])[None], p["k_test"], p["k_train"], float(p["radius"]))
+        assert np.array_equal(r[0], p[f"c{i}_Rs"]) and np.array_equal(t[0], p[f"c{i}_ts"])
+    table = np.zeros((92232, 4), dtype=np.int32)
+    table[int(p["depth_idx"][0])] = p["depth_bb"]
+    r, t = lift_pose_batch(np.asarray(p["depth_idx"])[None, :], rs, table, np.asarray(p["c2_bb"])[None], p["k_test"], p["k_train"],
+                           float(p["radius"]), depth_pred=812.5)
+    assert np.array_equal(r[0], p["depth_Rs"]) and np.array_equal(t[0], p["depth_ts"])
+    rng = np.random.RandomState(0)
+    D, k = 3000, 3
+    bbs = rng.randint(30, 500, (92232, 4)).astype(np.int32)
+    idcs = rng.randint(0, 92232, (D, k))
+    pb = np.stack([rng.uniform(0, 500, D), rng.uniform(0, 400, D), rng.uniform(20, 300, D), rng.uniform(20, 300, D)], 1)
+    pb[::3] = np.rint(pb[::3])                       # detectors mostly deliver integer pixel boxes
+    Rb, tb = lift_pose_batch(idcs, rs, bbs, pb, p["k_test"], p["k_train"], 700.0)
+    assert Rb.shape == (D, k, 3, 3) and tb.shape == (D, k, 3) and Rb.dtype == np.float64 and tb.dtype == np.float64
+    for d in range(D):
+        Rl, tl = lift_pose(idcs[d], rs, bbs, pb[d], p["k_test"], p["k_train"], 700.0)
+        assert np.array_equal(Rl, Rb[d]) and np.array_equal(tl, tb[d]), d
 
 
 def test_lift_pose_matches_reference(golden_dir):

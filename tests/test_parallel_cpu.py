@@ -35,7 +35,7 @@ class HostShard(P.ShardedCodebook):
     def _setup(self):
         self.device = torch.device("cpu")
 
-    def _local_match(self, z, k, upright):
+    def _local_match(self, z, k, upright, s_out, i_out):
         cos = O.cos_similarity(z.numpy(), self._local) if len(self._local) else np.zeros((z.shape[0], 0), np.float32)
         B = z.shape[0]
         s = np.full((B, k), -np.inf, np.float32)
@@ -48,9 +48,11 @@ class HostShard(P.ShardedCodebook):
             order = np.lexsort((gidx, -c))[:k]
             order = order[np.isfinite(c[order])]
             s[b, :len(order)], i[b, :len(order)] = c[order], gidx[order]
-        return torch.from_numpy(s), torch.from_numpy(i)
+        s_out.copy_(torch.from_numpy(s))
+        i_out.copy_(torch.from_numpy(i))
 
-    def _merge(self, all_s, all_i):
+    def _merge(self, packed):
+        all_s, all_i = packed[:, 0].contiguous().view(torch.float32), packed[:, 1]
         W, B, k = all_s.shape
         so, io = torch.empty((B, k)), torch.empty((B, k), dtype=torch.int32)
         for b in range(B):
@@ -128,6 +130,10 @@ def _router_case(rank, world):
     crops = torch.randint(0, 256, (10, 4, 4, 3), dtype=torch.uint8, generator=g)
     cls = np.array([3, 8, 11, 3, 99, 8, 8, 11, 3, 3])               # 99: unknown class
     s, i = router.route(crops, cls)
+    sh, ih = router.route_host(crops, cls, torch.device("cpu"))       # host routing: only the rank's own crops are touched
+    assert torch.equal(s, sh) and torch.equal(i, ih)
+    n_own = sum(len(sel) for _, sel in router.plan(cls))
+    assert n_own == sum(1 for c in cls if owner.get(int(c)) == rank) and n_own < len(cls)
     return s.numpy(), i.numpy()
 
 
