@@ -137,6 +137,34 @@ struct StageTimer {
   void release() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); used = 0; }
 };
 
+// Per-phase device timing of the training step: every mark opens a phase; the time until the next mark is charged to it.
+struct PhaseTimer {
+  static constexpr int kPhases = 7;   // 0 operand packs, 1 forward + loss, 2 wgrad GEMMs, 3 dgrad GEMMs, 4 glue, 5 fp32 dense / conv1 backward, 6 Adam
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> phase;
+  int used = 0;
+  void mark(int ph, cudaStream_t s) {
+    if (!enabled) return;
+    if (used == (int)ev.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; ev.push_back(e); phase.push_back(0); }
+    phase[used] = ph;
+    cudaEventRecord(ev[used++], s);
+  }
+  void reset() { used = 0; }
+  int read(float* ms, int cap) {
+    if (used < 2 || cap < kPhases) return 0;
+    for (int i = 0; i < kPhases; ++i) ms[i] = 0.f;
+    cudaEventSynchronize(ev[used - 1]);
+    for (int i = 0; i + 1 < used; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      if (phase[i] >= 0 && phase[i] < kPhases) ms[phase[i]] += t;
+    }
+    return kPhases;
+  }
+  void release() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); phase.clear(); used = 0; }
+};
+
 int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   AAE_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
   return AAE_OK;
@@ -216,6 +244,7 @@ struct aae_trainer {
   DevBuf dwm;           // gradient wrt merged sub-pixel weights
   TcTrainPlan* tc = nullptr;  // tensor-core backward plan (encoder and decoder created with AAE_PREC_TC_SPLIT)
   uint64_t packed_enc_version = 0, packed_dec_version = 0;   // master-weight versions the plan's dgrad operands were packed from
+  PhaseTimer ptimer;
 };
 
 // ============================================================================ misc
@@ -788,11 +817,21 @@ extern "C" int aae_trainer_destroy(aae_trainer* h) {
   h->dx_out.release(); h->grad_a.release(); h->grad_b.release(); h->dxup.release(); h->wt.release(); h->partials.release();
   h->bias_scratch.release(); h->sample_sums.release(); h->z.release(); h->dz.release(); h->rec.release(); h->dwm.release();
   tc_train_destroy(h->tc);
+  h->ptimer.release();
   delete h;
   return AAE_OK;
 }
 
 extern "C" int64_t aae_trainer_global_step(const aae_trainer* h) { return h ? h->step : -1; }
+
+extern "C" int aae_trainer_profile(aae_trainer* h, int enable, float* phase_ms_out, int capacity) {
+  AAE_REQUIRE(h != nullptr, "trainer handle is null");
+  DeviceGuard g(h->enc->device);
+  int n = 0;
+  if (phase_ms_out && capacity > 0) n = h->ptimer.read(phase_ms_out, capacity);
+  h->ptimer.enabled = enable != 0;
+  return n;
+}
 
 // wgrad of one conv layer: dW[tap,ci,co] = sum_pix X[pix@tap,ci] dY[pix,co]
 static int conv_wgrad(aae_trainer* h, const ConvLayer& L, const void* src, int B, const float* dy, float* dw, cudaStream_t s) {
@@ -867,6 +906,9 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
   const int nl = (int)E->conv.size(), nd = (int)D->conv.size();
   const int n_units = tc_train_num_units(P), n_dec = tc_train_num_decoder_units(P);
   AAE_REQUIRE(n_dec == nd && n_units == nd + nl - 1, "tensor-core trainer: plan does not match the network");
+  PhaseTimer& pt = h->ptimer;
+  pt.reset();
+  pt.mark(0, s);
   // ---- operands follow the fp32 master weights (Adam and set_weights change those) ----
   AAE_TRY(encoder_sync_tc(E, s));
   if (h->packed_dec_version != D->w_version || D->tc_stale) {
@@ -883,6 +925,7 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
     for (int u = n_dec; u < n_units; ++u) AAE_TRY(tc_train_pack_weights(P, u, E->conv[nl - 1 - (u - n_dec)].w.p, s));
     h->packed_enc_version = E->w_version;
   }
+  pt.mark(1, s);
   AAE_TRY(tc_train_begin_step(P, s));
   // ---- forward ----
   E->last_batch = B; E->last_was_tc = true;
@@ -893,6 +936,7 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
   AAE_TRY(launch_bootstrap_l2(h->rec.p, y, B, numel, k, h->sample_sums.p, loss_out, h->dx_out.p, s));
   AAE_TRY(launch_sigmoid_grad(h->dx_out.p, h->rec.p, (int64_t)B * numel, s));
   // ---- decoder backward ----
+  pt.mark(4, s);
   AAE_TRY(launch_bias_grad(h->dx_out.p, (int64_t)B * H * W, C, h->dec_b[nd].g.p, h->bias_scratch.p, s));
   AAE_TRY(tc_train_set_loss_grad(P, h->dx_out.p, B, s));
   float* raw = tc_train_raw(P);
@@ -900,19 +944,27 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
     const int l = nd - u;                        // decoder conv layer l (1-based; dec_k[l], D->conv[l-1])
     int is_enc, cin, cout, gh, gw, ndc;
     tc_train_unit_info(P, u, &is_enc, &cin, &cout, &gh, &gw, &ndc);
+    pt.mark(2, s);
     AAE_TRY(tc_train_unit_wgrad(P, u, B, h->dwm.p, s));
+    pt.mark(4, s);
     AAE_TRY(launch_unmerge_subpixel_grads(h->dwm.p, cin, cout, h->dec_k[l].g.p, s));
+    pt.mark(3, s);
     AAE_TRY(tc_train_unit_dgrad(P, u, B, s));
+    pt.mark(4, s);
     // masks with the ReLU of the producing layer (conv l-1, or dense_1) and folds that layer's bias gradient into the same pass;
     // dense_1's fp32 backward reads the masked gradient itself
     AAE_TRY(tc_train_finish(P, u, u + 1 < n_dec ? u + 1 : -1, B, false, /*keep_masked=*/l == 1, l > 1 ? h->dec_b[l - 1].g.p : nullptr, s));
   }
+  pt.mark(5, s);
   AAE_TRY(decoder_dense_backward(h, raw, B, s));
   // ---- encoder backward ----
   float* flat = E->conv.back().out.p;            // fp32 view of the last conv activation for the fp32 dense backward
+  pt.mark(4, s);
   AAE_TRY(tc_train_unpack_flat(P, B, flat, s));
   float* da = h->grad_a.p;
+  pt.mark(5, s);
   AAE_TRY(encoder_dense_backward(h, flat, B, da, s));
+  pt.mark(4, s);
   {
     const ConvLayer& L = E->conv.back();
     AAE_TRY(launch_bias_grad(da, (int64_t)B * L.out_h * L.out_w, L.out_c, h->enc_b[nl - 1].g.p, h->bias_scratch.p, s));
@@ -920,14 +972,20 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
   }
   for (int u = n_dec; u < n_units; ++u) {
     const int i = nl - 1 - (u - n_dec);          // encoder conv index (E->conv[i], enc_k[i]); i >= 1
+    pt.mark(2, s);
     AAE_TRY(tc_train_unit_wgrad(P, u, B, h->enc_k[i].g.p, s));
+    pt.mark(3, s);
     AAE_TRY(tc_train_unit_dgrad(P, u, B, s));
+    pt.mark(4, s);
     const bool last = u + 1 == n_units;
     // masked gradient of conv i-1's output (space-to-depth order, columns (cls, cin)); its column sums are conv i-1's bias gradient
     AAE_TRY(tc_train_finish(P, u, last ? -1 : u + 1, B, last, false, h->enc_b[i - 1].g.p, s));
   }
   // conv1 (Cin = 3, K = 75): fp32 wgrad from the plain-layout gradient the last unit wrote
-  return conv_wgrad(h, E->conv[0], x, B, tc_train_f32_out(P), h->enc_k[0].g.p, s);
+  pt.mark(5, s);
+  AAE_TRY(conv_wgrad(h, E->conv[0], x, B, tc_train_f32_out(P), h->enc_k[0].g.p, s));
+  pt.mark(6, s);   // closes the last phase; aae_train_step charges Adam to phase 6 and closes it with one more mark
+  return AAE_OK;
 }
 
 static int trainer_fwd_bwd(aae_trainer* h, const float* x, const float* y, int B, float* loss_out, cudaStream_t s) {
@@ -1037,6 +1095,7 @@ extern "C" int aae_train_step(aae_trainer* h, const float* x_dev, const float* y
     }
   if (ab.count) AAE_TRY(launch_adam_multi(ab, lr_t, h->b1, h->b2, h->eps, s));
   for (auto& L : h->dec->conv) L.wm_dirty = true;   // the merged sub-pixel weights follow the updated taps
+  h->ptimer.mark(6, s);
   // the masters changed in place: every packed copy (inference plans, trainer dgrad operands) is now one step behind
   h->enc->w_version += 1; h->dec->w_version += 1;
   h->enc->tc_stale = h->enc->tc != nullptr;

@@ -2,20 +2,29 @@
 """bench.py -- pose queries/sec (encode + codebook NN) on 128x128 crops (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision simt|tc]
+                    [--workload infer|sharded|routed|train] [--batches-per-step M]
 
-One "step" = one batch of 256 synthetic uint8 crops through the hot path: conv encoder -> latent -> fused
-L2-normalise + cosine match against the 92 232-row codebook -> (score, index) per crop  (BASELINE.json configs[1]).
-N > 1 (torchrun, one rank per GPU): independent replicas, every rank runs the same batch size ("weak" scaling); no
-data-path collective (queries are independent -- SURVEY.md section 8e row 1).
+infer (default, BASELINE.json configs[1]): one BATCH = 256 synthetic uint8 crops through the hot path: conv encoder -> latent
+    -> fused L2-normalise + cosine match against the 92 232-row codebook -> (score, index) per crop.  One "step" = M (default
+    16) such batches, every batch timed by its own CUDA-event pair with the L2 flushed in between, so that the default
+    20-step run times 320 batches (~0.8 s of device time) instead of 20.  N > 1 (torchrun, one rank per GPU): independent
+    replicas, every rank runs the same batch size ("weak" scaling); no data-path collective.  With N > 1
+    the line also carries short measurements of the two configurations that DO use NCCL ("sharded", "routed" keys).
+sharded (configs[4]): one 368 928-row codebook row-sharded over the ranks; per batch of 256 crops every rank encodes its
+    slice, NCCL all-gathers the latents, matches all queries against its rows, NCCL all-gathers the packed (score, index)
+    top-1 lists and merges.  The result is checked against the unsharded match in the same run.
+routed (configs[3]): 8 objects = 8 (encoder, codebook) pairs spread over the ranks, batch = 1024 mixed crops routed by class,
+    one all-reduce combines the per-crop results.
+train (configs[2]): one AAE training step at batch 64 on one GPU.
 
 Printed JSON (rank 0, one line):
-  value      whole-job queries/s with the crops already resident in HBM, device-timed (CUDA events per step, L2 flushed
-             between steps, max over ranks)
-  e2e        same metric through the public plugin call (Codebook.nearest_rotation) with HOST buffers: pinned H2D of the
-             crops and D2H of the indices inside the timed region
+  value      whole-job queries/s with the crops already resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e        same metric through the public plugin call with HOST buffers: pinned H2D of the crops and D2H of the indices
+             inside the timed region
   roofline   dominant kernel (largest share of the step): algorithmic FLOPs / measured duration vs MEASURED_PEAKS.json
   roofline_match   the fused codebook kernel against the HBM roofline
-  cpu_baseline     the CPU oracle (restated reference path, B=1 per call like the reference) on this box's cores
+  parity     one-off check outside the timed region: 10 000 crops, tensor-core path vs the exact-order fp32 path
+  cpu_baseline     the CPU oracle (restated reference path, variables resident, best thread count) on this box's cores
 --impl reference times that CPU path as the whole arm (TensorFlow is not installable offline: oracle port).
 """
 import argparse
@@ -33,14 +42,18 @@ sys.path.insert(0, ROOT)
 
 BATCH = 256
 N_ROWS = 92232
+N_ROWS_FINE = 368928            # configs[4]: 4x finer in-plane sampling (144 instead of 36 rotations per view)
 LATENT = 128
+ROUTED_BATCH = 1024
+ROUTED_OBJECTS = 8
 ENC_FLOP_PER_CROP = 2 * 2140667904
 LAYER_MAC_PER_CROP = [39321600, 838860800, 838860800, 419430400, 4194304]
 MATCH_BYTES = N_ROWS * LATENT * 4 + BATCH * LATENT * 4 + BATCH * 8
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures of this exact workload
-# (profiles/r01_ncu_*.txt; precision=tc, batch 256).  Algorithmic bytes beside them: conv2 = 537 MB (hi,lo) input + 3.3 MB
+# (profiles/r0*_ncu_*.txt; precision=tc, batch 256).  Algorithmic bytes beside them: conv2 = 537 MB (hi,lo) input + 3.3 MB
 # weights + 268 MB output = 808 MB; match = 47.36 MB.
 NCU_TRAFFIC = {"tc": {"conv1": 12688384 + 477692672, "conv2": 558148608 + 237978368, "match": 47414272 + 1536}}
+METRIC = "pose queries/sec (encode+codebook NN)"
 
 
 def peaks():
@@ -80,59 +93,355 @@ class ClockSampler(threading.Thread):
         except Exception as e:  # noqa: BLE001
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
+    def finish(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        return self.summary()
+
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def pct(xs, q):
+    s = sorted(xs)
+    return s[min(len(s) - 1, int(q * len(s)))]
+
+
 # ----------------------------------------------------------------------------------------------- CPU reference path
-def cpu_reference_qps(budget_s, batch=1, max_crops=4096):
-    """The reference's own data flow restated on the CPU (oracle/aae_oracle.py; TensorFlow cannot be installed offline):
-    x/255 -> conv encoder -> dense -> l2_normalize -> full [B, N] cosine row(s) -> host argmax, `batch` crops per call
-    (the reference calls session.run once per detection: batch=1)."""
-    import torch
-    from oracle import aae_oracle as O
-    torch.set_num_threads(os.cpu_count())
-    params = O.make_encoder_params(42)
-    E = O.make_codebook(7)
-    crops = O.make_crops_u8(1234, max(batch, 8))
-    O.nearest_rotation_idcs(crops[:batch], params, E)  # warm-up
-    done, t0 = 0, time.perf_counter()
-    while True:
-        O.nearest_rotation_idcs(crops[:batch], params, E)
-        done += batch
-        el = time.perf_counter() - t0
-        if el >= budget_s or done >= max_crops:
-            break
-    return done / el, done, el
+class CpuArm:
+    """The reference's own data flow restated on the CPU (oracle/aae_oracle.py ResidentCpuPath; TensorFlow cannot be installed
+    offline): x/255 -> conv encoder -> dense -> l2_normalize -> full [B, N] cosine matrix -> host argmax, with the variables
+    resident (as a tf.Session holds them) and the intra-op thread count chosen by a sweep -- the BEST CPU configuration found,
+    not os.cpu_count() threads on a one-crop convolution."""
+
+    def __init__(self):
+        from oracle import aae_oracle as O
+        self.O = O
+        self.path = O.ResidentCpuPath(O.make_encoder_params(42), O.make_codebook(7))
+        self.crops = O.make_crops_u8(1234, BATCH)
+        self.threads, self.table = {}, {}
+
+    def tune(self, batch):
+        if batch not in self.threads:
+            # big batches never win on a handful of threads: skip the slow end of the sweep (it would cost minutes on 128 cores)
+            lo = max(1, (os.cpu_count() or 1) // 16) if batch >= 32 else 1
+            t, sec, table = self.O.best_thread_count(lambda: self.path(self.crops[:batch]), repeats=1 if batch >= 64 else 2, min_threads=lo)
+            self.threads[batch], self.table[batch] = t, {k: round(batch / v, 1) for k, v in table.items()}
+        else:
+            import torch
+            torch.set_num_threads(self.threads[batch])
+        return self.threads[batch]
+
+    def qps(self, budget_s, batch, max_crops=1 << 30):
+        self.tune(batch)
+        done, t0 = 0, time.perf_counter()
+        while True:
+            self.path(self.crops[:batch])
+            done += batch
+            el = time.perf_counter() - t0
+            if el >= budget_s or done >= max_crops:
+                return done / el, done, el
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the restated reference CPU path on the metric's config (calls of up to 256 crops, configs[1]); every
+    step is one bounded sample of that workload.  Under torchrun rank 0 alone runs it."""
     if rank != 0:
         return
-    per_step_budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
-    qps_list, crops_total = [], 0
+    arm = CpuArm()
+    # sample size: one call per step, as many crops (<= 256) as ~4 s of CPU time buy at the tuned thread count
+    q32, _, _ = arm.qps(1.0, 32)
+    per_step_budget = max(1.0, min(6.0, 150.0 / max(1, args.steps + args.warmup)))
+    sample = int(min(BATCH, max(16, 16 * int(q32 * per_step_budget / 16))))
+    arm.tune(sample)
+    times = []
     for i in range(args.warmup + args.steps):
-        q, n, el = cpu_reference_qps(per_step_budget, batch=1, max_crops=256)
+        t0 = time.perf_counter()
+        arm.path(arm.crops[:sample])
         if i >= args.warmup:
-            qps_list.append((n, el))
-            crops_total += n
-    tot_n = sum(n for n, _ in qps_list)
-    tot_t = sum(t for _, t in qps_list)
-    v = tot_n / tot_t
-    out = {"impl": "reference", "metric": "pose queries/sec (encode+codebook NN)", "value": v, "unit": "queries/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+            times.append(time.perf_counter() - t0)
+    tot_t = sum(times)
+    v = sample * len(times) / tot_t
+    q1, n1, t1 = arm.qps(3.0, 1)
+    desc = ("%d crops per step in ONE call (the metric's config feeds 256-crop batches; bounded sample), torch CPU fp32, variables resident, "
+            "%d intra-op threads chosen by sweep %s; one crop per call (AePoseEstimator.process pattern): %.1f queries/s at %d threads"
+            % (sample, arm.threads[sample], arm.table[sample], q1, arm.threads[1]))
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(times)), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "configs[1]: single object, 128x128x3 uint8 crops, encoder + 92232-row codebook NN", "batch_per_call": 1,
-                      "note": "restated reference CPU path (oracle port; TensorFlow not installable offline), one crop per call like "
-                              "AePoseEstimator.process"},
-           "cpu_baseline": {"value": v, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
-                            "sample": "%d crops per step, B=1 per call, torch CPU fp32, %d threads" % (tot_n // max(1, args.steps), os.cpu_count())},
+           "config": {"workload": "configs[1]: single object, batch=256 synthetic 128x128x3 uint8 crops, encoder + codebook NN (92232 rows)",
+                      "batch_per_call": sample,
+                      "note": "restated reference CPU path (oracle port; TensorFlow not installable offline)"},
+           "cpu_baseline": {"value": v, "unit": "queries/s", "cores": os.cpu_count(), "threads": arm.threads[sample], "kind": "port", "sample": desc},
            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
 
-# ----------------------------------------------------------------------------------------------- ours
+# ----------------------------------------------------------------------------------------------- shared set-up
+def unit_rows(rng, n):
+    E = rng.standard_normal((n, LATENT))
+    return (E / np.linalg.norm(E, axis=1, keepdims=True)).astype(np.float32)
+
+
+def make_model(precision, max_batch, seed, n_rows=N_ROWS, num_cyclo=36, codebook_seed=None, with_codebook=True):
+    from augmentedautoencoder_b200.ae.codebook import Codebook
+    from augmentedautoencoder_b200.ae.encoder import Encoder
+    from augmentedautoencoder_b200.ae.session import placeholder
+    x_ph = placeholder(np.float32, [None, 128, 128, 3])
+    enc = Encoder(x_ph, LATENT, [128, 256, 512, 512], 5, [2, 2, 2, 2], False, precision=precision, max_batch=max_batch, seed=seed)
+    if not with_codebook:
+        return enc, None
+
+    class DS:
+        embedding_size = n_rows
+        _kw = {"num_cyclo": str(num_cyclo)}
+        viewsphere_for_embedding = np.zeros((n_rows, 3, 3))
+    cb = Codebook(enc, DS(), True, max_batch=max_batch, precision=precision)
+    E = unit_rows(np.random.RandomState(seed if codebook_seed is None else codebook_seed), n_rows)
+    E[num_cyclo - 1::num_cyclo] = E[0::num_cyclo]          # the duplicate end-point rows real codebooks hold
+    cb.embedding_normalized.assign(E)
+    return enc, cb
+
+
+def max_over_ranks(x, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ----------------------------------------------------------------------------------------------- configs[4]: row-sharded
+def measure_sharded(args, rank, world, dev, precision, steps, warmup):
+    """368 928-row codebook row-sharded over `world` ranks, 256 crops per batch.  Returns the result dict (same on all ranks)."""
+    import torch
+    import torch.distributed as dist
+    from augmentedautoencoder_b200 import _lib
+    from augmentedautoencoder_b200.parallel import ShardedCodebook, split_batch
+    lib = _lib.lib()
+    enc, _ = make_model(precision, BATCH, 42, with_codebook=False)
+    E = unit_rows(np.random.RandomState(11), N_ROWS_FINE)
+    E[143::144] = E[0::144]
+    sc = ShardedCodebook(E, num_cyclo=144, max_batch=BATCH, precision=precision, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(4321)
+    n_ring = 4
+    host = [torch.randint(0, 256, (BATCH, 128, 128, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_ring)]   # same on all ranks
+    a, e = split_batch(BATCH, world, rank)
+    mine = [h[a:e].to(dev) for h in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(i, ev=None):
+        marks = []
+
+        def mark():
+            if ev is not None:
+                m = torch.cuda.Event(enable_timing=True)
+                m.record()
+                marks.append(m)
+        mark()
+        z_loc = enc.encode_device(mine[i % n_ring])
+        mark()
+        if world > 1:
+            per = -(-BATCH // world)
+            pad = z_loc if z_loc.shape[0] == per else torch.cat([z_loc, z_loc.new_zeros((per - z_loc.shape[0], LATENT))])
+            all_z = torch.empty((world * per, LATENT), dtype=z_loc.dtype, device=dev)
+            dist.all_gather_into_tensor(all_z, pad.contiguous())
+            z = all_z[:BATCH]
+        else:
+            z = z_loc
+        mark()
+        pk = torch.empty((2, BATCH, 1), dtype=torch.int32, device=dev)
+        s, idx = pk[0].view(torch.float32), pk[1]
+        sc._local_match(z, 1, False, s, idx)
+        mark()
+        if world > 1:
+            allpk = torch.empty((world * 2, BATCH, 1), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(allpk, pk)
+            mark()
+            s, idx = sc._merge(allpk.view(world, 2, BATCH, 1))
+        else:
+            mark()
+        mark()
+        if ev is not None:
+            ev.append(marks)
+        return s, idx, z
+
+    # in-run check against the unsharded match (the same rows in one table on this GPU), bit for bit
+    s, idx, z = step(0)
+    _, full = make_model(precision, BATCH, 42, n_rows=N_ROWS_FINE, num_cyclo=144, codebook_seed=11)
+    full._encoder = enc
+    s1, i1 = full.match_device(z.contiguous())
+    ok = torch.tensor([int(torch.equal(idx, i1) and torch.equal(s, s1))], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    full.close()
+    del full
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = lib.aae_launch_count()
+    ev = []
+    for i in range(steps):
+        flush.zero_()
+        step(i, ev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = lib.aae_launch_count() - l0
+    phases = np.array([[m[j].elapsed_time(m[j + 1]) for j in range(5)] for m in ev])          # encode, gather z, match, gather top-k, merge
+    total_ms = max_over_ranks(float(phases.sum()), dev, world)
+    # e2e: host crops of this rank's slice up, indices down, every batch
+    for i in range(2):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        mine[i % n_ring].copy_(host[i % n_ring][a:e], non_blocking=True)
+        _, idx, _ = step(i)
+        idx_host = idx.cpu()
+    t_e2e = max_over_ranks(time.perf_counter() - t0, dev, world)
+    assert idx_host.shape == (BATCH, 1)
+    med = np.median(phases, axis=0)
+    res = {"workload": "configs[4]: single object, %d-row codebook row-sharded over %d GPU(s), batch=256, encoder split over ranks, "
+                       "NCCL all-gather of latents and of packed (score, index) top-1, merge" % (N_ROWS_FINE, world),
+           "value": BATCH * steps / (total_ms * 1e-3), "unit": "queries/s", "ms_per_batch": total_ms / steps, "steps": steps,
+           "phase_ms_median": {"encode_slice": med[0], "allgather_latents": med[1], "match_shard": med[2], "allgather_topk": med[3], "merge": med[4]},
+           "collective_share": float((med[1] + med[3]) / med.sum()), "rows_per_rank": sc.hi - sc.lo,
+           "collective_bytes_per_rank": {"latents": (e - a) * LATENT * 4, "topk": BATCH * 8},
+           "sharded_equals_unsharded": bool(int(ok.item())), "gpu_launches": int(launches),
+           "e2e": {"value": BATCH * steps / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": (e - a) * 128 * 128 * 3, "d2h_bytes_per_step": BATCH * 4}}
+    sc.close()
+    enc.close()
+    return res
+
+
+# ----------------------------------------------------------------------------------------------- configs[3]: routed
+def measure_routed(args, rank, world, dev, precision, steps, warmup):
+    """8 objects x 92 232-row codebooks spread over the ranks, 1024 mixed crops per batch routed by class id."""
+    import torch
+    import torch.distributed as dist
+    from augmentedautoencoder_b200 import _lib
+    from augmentedautoencoder_b200.parallel import ObjectRouter, owner_of_class
+    lib = _lib.lib()
+    classes = list(range(ROUTED_OBJECTS))
+    own = owner_of_class(classes, world)
+    cbs, keep = {}, []
+    for c in classes:
+        if own[c] == rank:
+            enc_c, cb_c = make_model(precision, BATCH, 42 + c, codebook_seed=7 + c)
+            cbs[c] = cb_c
+            keep.append(enc_c)
+    router = ObjectRouter(cbs, classes)
+    g = torch.Generator(device="cpu").manual_seed(999)
+    n_ring = 2
+    host = [torch.randint(0, 256, (ROUTED_BATCH, 128, 128, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_ring)]
+    cls = [np.random.RandomState(99 + i).randint(0, ROUTED_OBJECTS, ROUTED_BATCH) for i in range(n_ring)]
+    # device-resident variant: this rank's own crops already in HBM, grouped by class
+    resident = []
+    for i in range(n_ring):
+        parts = [(c, torch.from_numpy(sel).to(dev), host[i][torch.from_numpy(sel)].to(dev)) for c, sel in router.plan(cls[i])]
+        resident.append(parts)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device(i):
+        parts = [(pos,) + tuple(router._run_class(c, crops)) for c, pos, crops in resident[i % n_ring]]
+        return router._exchange(ROUTED_BATCH, parts, dev)
+
+    s, idx = step_device(0)
+    ok = int((idx >= 0).all())
+    for c, pos, crops in resident[0]:                      # every owned position holds its own model's answer
+        s_c, i_c = cbs[c].nearest_idx_device(crops)
+        ok &= int(torch.equal(idx[pos], i_c[:, 0]) and torch.equal(s[pos], s_c[:, 0]))
+    sh, ih = router.route_host(host[0], cls[0], dev)       # host-routed call gives the same complete answer
+    ok &= int(torch.equal(ih, idx) and torch.equal(sh, s))
+    okt = torch.tensor([ok], device=dev)
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    for i in range(warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = lib.aae_launch_count()
+    ev = []
+    for i in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_device(i)
+        b.record()
+        ev.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = lib.aae_launch_count() - l0
+    total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), dev, world)
+    for i in range(2):
+        router.route_host(host[i % n_ring], cls[i % n_ring], dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n_own = sum(len(sel) for _, sel in router.plan(cls[0]))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        _, idx = router.route_host(host[i % n_ring], cls[i % n_ring], dev)
+        idx_host = idx.cpu()
+    t_e2e = max_over_ranks(time.perf_counter() - t0, dev, world)
+    assert idx_host.shape == (ROUTED_BATCH,)
+    res = {"workload": "configs[3]: %d objects x %d-row codebooks spread over %d GPU(s) (%d per GPU), batch=%d mixed crops routed by class, "
+                       "one all-reduce of [2,B] int32 combines the results" % (ROUTED_OBJECTS, N_ROWS, world, len(cbs), ROUTED_BATCH),
+           "value": ROUTED_BATCH * steps / (total_ms * 1e-3), "unit": "queries/s", "ms_per_batch": total_ms / steps, "steps": steps,
+           "own_crops_rank0": int(n_own), "routing_checked": bool(int(okt.item())), "gpu_launches": int(launches),
+           "e2e": {"value": ROUTED_BATCH * steps / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": int(n_own) * 128 * 128 * 3,
+                   "d2h_bytes_per_step": ROUTED_BATCH * 4, "api": "ObjectRouter.route_host(pinned mixed batch, class ids): each rank uploads only its own crops"}}
+    for cb in cbs.values():
+        cb.close()
+    for e_ in keep:
+        e_.close()
+    return res
+
+
+# ----------------------------------------------------------------------------------------------- ours: configs[1]
+def parity_check(sess, cb, dev, n_queries=10000):
+    """One-off, outside every timed region: n_queries structured-random crops through the tensor-core path (the one timed above)
+    and through the library's exact-order fp32 CUDA-core path (pinned to the oracle by tests/test_gpu_a_parity.py)."""
+    import torch
+    from augmentedautoencoder_b200 import _lib
+    enc0, cb0 = make_model(_lib.PREC_FP32_SIMT, BATCH, 42)
+    enc0.load_weights(cb._encoder.get_weights())
+    cb0.embedding_normalized.assign(cb.embedding_normalized.value())
+    g = torch.Generator(device="cpu").manual_seed(77)
+    mism, max_d, done, near = 0, 0.0, 0, 0
+    while done < n_queries:
+        n = min(BATCH, n_queries - done)
+        coarse = torch.randint(0, 256, (n, 8, 8, 3), generator=g, dtype=torch.int32)
+        img = coarse.repeat_interleave(16, 1).repeat_interleave(16, 2) + torch.randint(-40, 41, (n, 128, 128, 3), generator=g, dtype=torch.int32)
+        crops = img.clamp_(0, 255).to(torch.uint8).to(dev)
+        s1, i1 = cb.nearest_idx_device(crops)
+        z0 = enc0.encode_device(crops)
+        s0, i0 = cb0.match_device(z0)
+        bad = (i1[:, 0] != i0[:, 0])
+        nb = int(bad.sum())
+        if nb:
+            # score of the tensor-core winner under the fp32 path: a flip is a near-tie if the two candidates differ by < 2e-6
+            cos0 = torch.nn.functional.normalize(z0[bad], dim=1) @ torch.from_numpy(cb.embedding_normalized.value()).to(dev)[i1[bad, 0].long()].T
+            gap = (s0[bad, 0] - cos0.diagonal()).abs()
+            near += int((gap < 2e-6).sum())
+        mism += nb
+        max_d = max(max_d, float((s1[:, 0] - s0[:, 0]).abs().max()))
+        done += n
+    cb0.close()
+    enc0.close()
+    return {"queries": n_queries, "index_mismatches": mism, "mismatches_with_fp32_score_gap_below_2e-6": near, "max_abs_dcos": max_d,
+            "against": "this library's AAE_PREC_FP32_SIMT path (exact fp32 operation order; itself index-exact vs the CPU oracle in tests/)"}
+
+
 def run_ours(args, rank, world, local_rank):
     import ctypes as C
 
@@ -147,110 +456,106 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()   # nobody loads the library before rank 0 has (re)built it
     dev = torch.device("cuda", local_rank)
-    from augmentedautoencoder_b200.ae.codebook import Codebook
-    from augmentedautoencoder_b200.ae.encoder import Encoder
-    from augmentedautoencoder_b200.ae.session import Session, placeholder
-
+    from augmentedautoencoder_b200.ae.session import Session
     precision = {"simt": _lib.PREC_FP32_SIMT, "tc": _lib.PREC_TC_SPLIT}[args.precision]
-    rng = np.random.RandomState(42)
+    lib = _lib.lib()
     sess = Session(device=local_rank)
-    x_ph = placeholder(np.float32, [None, 128, 128, 3])
-    enc = Encoder(x_ph, LATENT, [128, 256, 512, 512], 5, [2, 2, 2, 2], False, precision=precision, max_batch=BATCH, seed=42)
 
-    class DS:
-        embedding_size = N_ROWS
-        _kw = {"num_cyclo": "36"}
-        viewsphere_for_embedding = np.zeros((N_ROWS, 3, 3))
-    cb = Codebook(enc, DS(), True, max_batch=BATCH, precision=precision)
-    E = rng.standard_normal((N_ROWS, LATENT))
-    E = (E / np.linalg.norm(E, axis=1, keepdims=True)).astype(np.float32)
-    E[35::36] = E[0::36]
-    cb.embedding_normalized.assign(E)
+    if args.workload in ("sharded", "routed"):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        fn = measure_sharded if args.workload == "sharded" else measure_routed
+        res = fn(args, rank, world, dev, precision, args.steps, args.warmup)
+        clocks = sampler.finish()
+        if rank == 0:
+            out = {"metric": METRIC, "value": res["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                   "ms_per_step": res["ms_per_batch"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                   "dtype": "f32" if args.precision == "simt" else "f32 via split-fp16 tensor-core products (3x, fp32 accumulate)",
+                   "data": "synthetic", "config": {"workload": res["workload"], "precision": args.precision,
+                                                   "l2": "256 MiB memset between timed batches (untimed)"},
+                   "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clocks, "cpu_baseline": None, "roofline": None,
+                   "detail": {k: v for k, v in res.items() if k not in ("value", "unit", "e2e", "workload", "gpu_launches")}}
+            print(json.dumps(out))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
+    enc, cb = make_model(precision, BATCH, 42)
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     n_ring = 4
     host_crops = [torch.randint(0, 256, (BATCH, 128, 128, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_ring)]
     dev_crops = [c.to(dev) for c in host_crops]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    lib = _lib.lib()
     enc_h, cb_h = enc.handle(dev), cb.handle(dev)
+    M = max(1, args.batches_per_step)
+    n_batches = args.steps * M
 
-    def step_device(i):
+    def batch_device(i):
         return cb.nearest_idx_device(dev_crops[i % n_ring])
 
     # ---- warm-up (also builds handles / packs operands) ----
-    for i in range(args.warmup):
-        step_device(i)
+    for i in range(args.warmup * M):
+        batch_device(i)
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- timed: device-resident inputs, per-step CUDA events, L2 flushed between steps ----
+    # ---- timed: device-resident inputs, one CUDA-event pair per batch, L2 flushed between batches ----
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = lib.aae_launch_count()
     evs = []
-    for i in range(args.steps):
+    for i in range(n_batches):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        step_device(i)
+        batch_device(i)
         b.record()
         evs.append((a, b))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     launches = lib.aae_launch_count() - launches0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    batch_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = max_over_ranks(sum(batch_ms), dev, world)
 
     # ---- e2e: public plugin call with host buffers (pinned H2D + D2H inside the timed region) ----
     for i in range(2):
         cb.nearest_rotation(sess, host_crops[i % n_ring], return_idcs=True)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    # The plugin's streaming call: batch i+1's pinned H2D copy is in flight while batch i computes; every step's H2D copy and
+    # The plugin's streaming call: batch i+1's pinned H2D copy is in flight while batch i computes; every batch's H2D copy and
     # D2H read of the indices happen inside the timed region (wall clock around the whole loop, results collected on the host).
     for i in range(2):
         cb.nearest_rotation_async(sess, host_crops[i % n_ring]).result()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     pending = cb.nearest_rotation_async(sess, host_crops[0])
-    for i in range(1, args.steps + 1):
-        nxt = cb.nearest_rotation_async(sess, host_crops[i % n_ring]) if i < args.steps else None
+    for i in range(1, n_batches + 1):
+        nxt = cb.nearest_rotation_async(sess, host_crops[i % n_ring]) if i < n_batches else None
         idcs = pending.result()          # numpy int64 [BATCH] on the host
         pending = nxt
-    t_async = time.perf_counter() - t0
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev, world)
     t_e2e = []
-    for i in range(args.steps):
+    for i in range(min(n_batches, 40)):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         idcs = cb.nearest_rotation(sess, host_crops[i % n_ring], return_idcs=True)  # blocking call: copy, compute, read back in series
         t_e2e.append(time.perf_counter() - t0)
     assert idcs.shape == (BATCH,)
-    e2e_blocking_s = sum(t_e2e)
-    e2e_s = torch.tensor([t_async], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    clocks = sampler.finish()
 
     # ---- per-stage device timing for the roofline lines (separate profiled passes, cudaEvents inside the library) ----
     buf = (C.c_float * 16)()
     lib.aae_encoder_profile(enc_h, 1, None, 0)
     lib.aae_codebook_profile(cb_h, 1, None, 0)
     enc_stage, match_ms = [], []
-    for i in range(max(3, min(args.steps, 10))):
+    for i in range(20):
         flush.zero_()
-        step_device(i)
+        batch_device(i)
         torch.cuda.synchronize()
         n = lib.aae_encoder_profile(enc_h, 1, buf, 16)
         enc_stage.append([buf[j] for j in range(n)])
@@ -259,13 +564,27 @@ def run_ours(args, rank, world, local_rank):
     lib.aae_encoder_profile(enc_h, 0, None, 0)
     lib.aae_codebook_profile(cb_h, 0, None, 0)
 
+    parity = None
+    if world == 1 and args.precision == "tc" and not args.no_parity:
+        parity = parity_check(sess, cb, dev)
+    extra = {}
+    if world > 1 and not args.no_collective_workloads:
+        # the two BASELINE configurations whose timed region contains a collective (short runs, same box, same ranks)
+        cb.close()
+        enc.close()
+        del dev_crops, flush
+        torch.cuda.empty_cache()
+        extra["sharded"] = measure_sharded(args, rank, world, dev, precision, 40, 5)
+        extra["routed"] = measure_routed(args, rank, world, dev, precision, 20, 3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
     ms_per_step = total_ms / args.steps
-    value = world * BATCH * args.steps / (total_ms * 1e-3)
+    ms_per_batch = total_ms / n_batches
+    value = world * BATCH * n_batches / (total_ms * 1e-3)
     stage_med = [statistics.median(col) for col in zip(*enc_stage)] if enc_stage and enc_stage[0] else []
     roof = None
     if stage_med:
@@ -280,33 +599,44 @@ def run_ours(args, rank, world, local_rank):
                 "traffic": traffic, "peak_source": pk["src"] + " bf16 burst", "stage_ms": stage_med,
                 "tensor_pipe": {"products_per_mac": products, "issued_tflops": ach * products, "issued_frac_of_peak": ach * products / peak,
                                 "why": "fp32-grade results need hi*hi + hi*lo + lo*hi on fp16 tensor cores; `achieved` counts each MAC once"},
-                "share_of_step": stage_med[dom] / ms_per_step,
-                "note": "algorithmic FLOPs (2*MAC) of the layer / cudaEvent duration; precision=%s" % args.precision}
+                "share_of_step": stage_med[dom] / ms_per_batch,
+                "whole_encoder": {"achieved": ENC_FLOP_PER_CROP * BATCH / (sum(stage_med) * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                  "frac": ENC_FLOP_PER_CROP * BATCH / (sum(stage_med) * 1e-3) / 1e12 / peak},
+                "note": "algorithmic FLOPs (2*MAC) of the layer / cudaEvent duration (median of 20 profiled batches); precision=%s" % args.precision}
     mm = statistics.median(match_ms) if match_ms else float("nan")
     ach_b = MATCH_BYTES / (mm * 1e-3) / 1e9
     roof_match = {"kernel": "fused codebook match (l2norm + scores + argmax)", "bound": "hbm", "achieved": ach_b, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                  "frac": ach_b / pk["hbm_gbs"], "traffic": NCU_TRAFFIC.get(args.precision, {}).get("match"), "ms": mm, "bytes": MATCH_BYTES, "peak_source": pk["src"]}
+                  "frac": ach_b / pk["hbm_gbs"], "traffic": NCU_TRAFFIC.get(args.precision, {}).get("match"), "ms": mm, "bytes": MATCH_BYTES,
+                  "peak_source": pk["src"],
+                  "regime": "B=256 with 3 split-fp16 products per MAC is tensor-bound (18.1 GFLOP issued ~= 10.7 us at the bf16 burst peak > 7.2 us HBM "
+                            "floor); B <= 128 is HBM-bound"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        q1, n1, t1 = cpu_reference_qps(12.0, batch=1)
-        q64, n64, t64 = cpu_reference_qps(6.0, batch=64)
-        cpu = {"value": q1, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "%d crops in %.1f s, one crop per call (reference calling pattern), torch CPU fp32 oracle; batched B=64: %.1f queries/s"
-                         % (n1, t1, q64)}
-    out = {"metric": "pose queries/sec (encode+codebook NN)", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        arm = CpuArm()
+        q64, n64, t64 = arm.qps(10.0, 64)
+        q1, n1, t1 = arm.qps(5.0, 1)
+        cpu = {"value": q64, "unit": "queries/s", "cores": os.cpu_count(), "threads": arm.threads[64], "kind": "port",
+               "sample": "%d crops in %.1f s, 64 crops per call (bounded sample of the 256-crop batches), torch CPU fp32 oracle with resident variables, "
+                         "%d intra-op threads chosen by sweep %s; one crop per call (the reference's per-detection pattern): %.1f queries/s at %d threads"
+                         % (n64, t64, arm.threads[64], arm.table[64], q1, arm.threads[1])}
+    out = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32" if args.precision == "simt" else "f32 via split-fp16 tensor-core products (3x, fp32 accumulate)",
            "data": "synthetic",
            "config": {"workload": "configs[1]: single object, batch=256 synthetic 128x128x3 uint8 crops, encoder + fused codebook NN (92232 rows)",
-                      "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": "dp%d (independent replicas)" % world,
-                      "l2": "256 MiB memset between timed steps (untimed) so weights/codebook/crops come from HBM",
+                      "batch_per_gpu": BATCH, "global_batch": BATCH * world, "batches_per_step": M, "timed_batches": n_batches,
+                      "parallelism": "dp%d (independent replicas)" % world,
+                      "l2": "256 MiB memset between timed batches (untimed) so weights/codebook/crops come from HBM",
                       "precision": args.precision},
-           "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": BATCH * 128 * 128 * 3,
-                   "d2h_bytes_per_step": BATCH * 4, "api": "Codebook.nearest_rotation_async(session, pinned uint8 crops).result(), one batch in flight ahead",
-                   "blocking_call_value": world * BATCH * args.steps / e2e_blocking_s,
+           "ms_per_batch": {"mean": ms_per_batch, "median": statistics.median(batch_ms), "p10": pct(batch_ms, 0.1), "p90": pct(batch_ms, 0.9),
+                            "min": min(batch_ms), "rank": 0},
+           "e2e": {"value": world * BATCH * n_batches / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": M * BATCH * 128 * 128 * 3,
+                   "d2h_bytes_per_step": M * BATCH * 4, "api": "Codebook.nearest_rotation_async(session, pinned uint8 crops).result(), one batch in flight ahead",
+                   "blocking_call_value": world * BATCH * len(t_e2e) / sum(t_e2e),
                    "blocking_api": "Codebook.nearest_rotation(session, pinned uint8 crops, return_idcs=True), L2 flushed before each call"},
-           "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "roofline_match": roof_match,
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_match": roof_match, "parity": parity,
            "cpu_baseline": cpu}
+    out.update(extra)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -315,6 +645,8 @@ def run_ours(args, rank, world, local_rank):
 def run_train(args, rank, world, local_rank):
     """BASELINE.json configs[2]: AAE training step (encode + decode + bootstrapped L2 + backward + TF-Adam), batch 64, one GPU.
     Not the headline metric: an extra line for the results table (python bench.py --workload train)."""
+    import ctypes as C
+
     import torch
     from augmentedautoencoder_b200 import _lib, build_ext
     build_ext.build()
@@ -331,21 +663,57 @@ def run_train(args, rank, world, local_rank):
     enc = Encoder(x, LATENT, [128, 256, 512, 512], 5, [2, 2, 2, 2], False, is_training=True, max_batch=B, precision=prec)
     dec = Decoder(y, enc.z, [512, 512, 256, 128], 5, [2, 2, 2, 2], "L2", 4, False, False, is_training=True, max_batch=B, precision=prec)
     top = TrainOp(AE(enc, dec, 0, 0), 2e-4)
-    g = torch.Generator(device="cuda").manual_seed(1234)
-    xb = torch.rand((B, 128, 128, 3), device="cuda", generator=g)
-    yb = torch.rand((B, 128, 128, 3), device="cuda", generator=g)
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    n_ring = 4
+    host = [(torch.rand((B, 128, 128, 3), generator=g).pin_memory(), torch.rand((B, 128, 128, 3), generator=g).pin_memory()) for _ in range(n_ring)]
+    devb = [(a.cuda(), b.cuda()) for a, b in host]
     lib = _lib.lib()
-    for _ in range(max(args.warmup, 3)):
-        top.step_device(xb, yb)
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        top.step_device(*devb[i % n_ring])
     torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     l0 = lib.aae_launch_count()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.steps):
-        loss = top.step_device(xb, yb)
-    b.record()
+    evs = []
+    for i in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        loss = top.step_device(*devb[i % n_ring])
+        b.record()
+        evs.append((a, b))
     torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / args.steps
+    launches = int(lib.aae_launch_count() - l0)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    ms = sum(step_ms) / args.steps
+    # e2e: the batch comes from pinned host memory and the loss goes back to the host every step
+    xd, yd = torch.empty_like(devb[0][0]), torch.empty_like(devb[0][1])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        xd.copy_(host[i % n_ring][0], non_blocking=True)
+        yd.copy_(host[i % n_ring][1], non_blocking=True)
+        loss_host = float(top.step_device(xd, yd))
+    t_e2e = time.perf_counter() - t0
+    clocks = sampler.finish()
+    # per-phase device time (separate profiled steps)
+    phases = None
+    h = top.trainer(torch.device("cuda", local_rank))
+    if args.precision == "tc":
+        buf = (C.c_float * 8)()
+        lib.aae_trainer_profile(h, 1, None, 0)
+        rows = []
+        for i in range(10):
+            top.step_device(*devb[i % n_ring])
+            torch.cuda.synchronize()
+            n = lib.aae_trainer_profile(h, 1, buf, 8)
+            if n:
+                rows.append([buf[j] for j in range(n)])
+        lib.aae_trainer_profile(h, 0, None, 0)
+        if rows:
+            med = np.median(np.array(rows), axis=0)
+            names = ["operand_packs", "forward_and_loss", "wgrad_gemms", "dgrad_gemms", "glue", "fp32_dense_and_conv1_backward", "adam"]
+            phases = {k: float(v) for k, v in zip(names, med)}
     flop = 3 * (4.2813e9 + 17.1002e9) * B                   # the reference's count (5x5 convs on the upsampled maps)
     pk = peaks()
     tc = args.precision == "tc"
@@ -354,13 +722,19 @@ def run_train(args, rank, world, local_rank):
                     "multiply-adds" + (", each as 3 split-fp16 tensor-core products" if tc else ", fp32 CUDA cores")}
     if tc:
         roof["peak"] = pk["tf_sustained"]
-        roof["peak_source"] = pk["src"]
+        roof["peak_source"] = pk["src"] + " bf16 sustained"
         roof["frac"] = roof["achieved"] / roof["peak"]
     print(json.dumps({"metric": "AAE training steps/sec (batch 64, 128x128)", "value": 1e3 / ms, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
-                      "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": "f32 (split-fp16 x3 on tcgen05)" if tc else "f32",
+                      "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32 (split-fp16 x3 on tcgen05)" if tc else "f32",
                       "data": "synthetic", "images_per_s": B * 1e3 / ms,
-                      "config": {"workload": "configs[2]: AAE training step, batch=64", "precision": "tc_split" if tc else "fp32_simt"},
-                      "gpu_launches": int(lib.aae_launch_count() - l0), "loss": float(loss), "roofline": roof}))
+                      "ms_per_step_stats": {"median": statistics.median(step_ms), "p10": pct(step_ms, 0.1), "p90": pct(step_ms, 0.9)},
+                      "config": {"workload": "configs[2]: AAE training step, batch=64", "precision": "tc_split" if tc else "fp32_simt",
+                                 "l2": "4 batches of 2 x 12.6 MB inputs cycle; the step's own 1.3 GB of activations and 0.8 GB of Adam traffic exceed L2"},
+                      "e2e": {"value": args.steps / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": 2 * B * 128 * 128 * 3 * 4, "d2h_bytes_per_step": 4,
+                              "api": "TrainOp.step_device on batches copied from pinned host memory, float(loss) read back every step"},
+                      "gpu_launches": launches, "launches_per_step": launches / args.steps, "loss": float(loss), "loss_e2e": loss_host,
+                      "clocks": clocks, "cpu_baseline": None, "phase_ms": phases, "roofline": roof}))
 
 
 def main():
@@ -371,17 +745,20 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("AAE_BENCH_PRECISION", "tc"), choices=["simt", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-collective-workloads", action="store_true")
+    ap.add_argument("--batches-per-step", type=int, default=16)
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "sharded", "routed"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload == "train":
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    elif args.workload == "train":
         if rank == 0:
             run_train(args, rank, world, local_rank)
-    elif args.impl == "reference":
-        run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -186,6 +186,11 @@ AAE_API int aae_trainer_forward_backward(aae_trainer* h, const float* x_dev, con
 /* which: 0 = encoder, 1 = decoder; layer as in *_set_weights. */
 AAE_API int aae_trainer_get_grads(aae_trainer* h, int which, int layer, float* kernel_grad_any, float* bias_grad_any, void* stream);
 AAE_API int64_t aae_trainer_global_step(const aae_trainer* h);
+/* Per-phase device time of the last training step (cudaEvents on the launching stream; tensor-core trainer only):
+ * phase_ms_out[0..6] = operand packs, forward + loss, wgrad GEMMs, dgrad GEMMs, glue (masks / bias sums / re-splits),
+ * fp32 backward of the dense layers and of conv1, Adam.  Same enable/read contract as aae_encoder_profile; returns the
+ * number of values written (0 when nothing was recorded).  Measurement aid for bench.py --workload train. */
+AAE_API int aae_trainer_profile(aae_trainer* h, int enable, float* phase_ms_out, int capacity);
 
 /* ---------------------------------------------------------------- Crop extraction ----------
  * Batched AePoseEstimator.extract_square_patch(black_borders=True) + cv2.resize(INTER_LINEAR)

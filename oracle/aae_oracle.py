@@ -574,13 +574,13 @@ class ResidentCpuPath:
         return np.argmax(self.cos(crops), axis=1)
 
 
-def best_thread_count(fn, candidates=(1, 2, 4, 8, 16, 32, 64, 128, 256), repeats: int = 2):
-    """Times ``fn()`` under torch.set_num_threads(t) for every candidate t <= the machine's cores and leaves torch set to the
-    fastest.  Returns (threads, seconds per call at that setting, {t: seconds})."""
+def best_thread_count(fn, candidates=(1, 2, 4, 8, 16, 32, 64, 128, 256), repeats: int = 2, min_threads: int = 1):
+    """Times ``fn()`` under torch.set_num_threads(t) for every candidate min_threads <= t <= the machine's cores and leaves
+    torch set to the fastest.  Returns (threads, seconds per call at that setting, {t: seconds})."""
     import os
     import time
     ncpu = os.cpu_count() or 1
-    cands = sorted({t for t in candidates if t <= ncpu} | {ncpu})
+    cands = sorted({t for t in candidates if min_threads <= t <= ncpu} | {ncpu})
     table = {}
     for t in cands:
         torch.set_num_threads(t)
