@@ -477,7 +477,7 @@ extern "C" int aae_codebook_create(int device, const float* embedding_any, int64
     cudaError_t e = cudaMemcpy(h->E.p, embedding_any, (size_t)n_rows * latent * sizeof(float), cudaMemcpyDefault);
     if (e != cudaSuccess) { set_error("codebook upload failed: %s", cudaGetErrorString(e)); st = AAE_ERR_CUDA; }
   }
-  if (st == AAE_OK && precision == AAE_PREC_TC_SPLIT) st = tc_codebook_create(device, h->E.p, n_rows, latent, max_batch, &h->tc);
+  if (st == AAE_OK && precision == AAE_PREC_TC_SPLIT) st = tc_codebook_create(device, h->E.p, n_rows, latent, num_cyclo, max_batch, &h->tc);
   if (st != AAE_OK) { aae_codebook_destroy(h); return st; }
   *out = h;
   return AAE_OK;
@@ -517,14 +517,15 @@ extern "C" int aae_codebook_match(aae_codebook* h, const float* z_dev, int batch
   AAE_REQUIRE(k >= 1 && k <= h->n_rows, "k=%d outside [1, n_rows]", k);
   DeviceGuard g(h->device);
   cudaStream_t s = (cudaStream_t)stream;
+  // tensor-core kernel: k <= 8, with or without `upright` (codebook.py:64-71) -- one fused launch, nothing else
+  if (h->tc && k <= tc_codebook_max_k() && (!upright || h->row_offset % h->num_cyclo == 0)) {
+    h->timer.reset();
+    h->timer.mark(s);
+    AAE_TRY(tc_codebook_match(h->tc, z_dev, batch, h->row_offset, k, upright, scores_out_dev, idx_out_dev, s));
+    h->timer.mark(s);
+    return AAE_OK;
+  }
   if (k == 1) {
-    if (h->tc && !upright) {
-      h->timer.reset();
-      h->timer.mark(s);
-      AAE_TRY(tc_codebook_match(h->tc, h->E.p, z_dev, batch, h->row_offset, h->num_cyclo, upright, scores_out_dev, idx_out_dev, s));
-      h->timer.mark(s);
-      return AAE_OK;
-    }
     h->timer.reset();
     h->timer.mark(s);
     AAE_TRY(launch_l2_normalize(z_dev, batch, h->latent, h->zq.p, s));

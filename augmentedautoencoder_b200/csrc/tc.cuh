@@ -53,9 +53,11 @@ int tc_train_unit_dgrad(TcTrainPlan* h, int u, int B, cudaStream_t s);
 int tc_train_finish(TcTrainPlan* h, int u, int next, int B, bool want_f32, bool keep_masked, float* db_out, cudaStream_t s);
 int tc_train_unpack_flat(TcTrainPlan* h, int B, float* out, cudaStream_t s);
 
-int tc_codebook_create(int device, const float* E_dev, int64_t n_rows, int latent, int max_batch, TcCodebook** out);
+int tc_codebook_create(int device, const float* E_dev, int64_t n_rows, int latent, int num_cyclo, int max_batch, TcCodebook** out);
 void tc_codebook_destroy(TcCodebook* h);
-int tc_codebook_match(TcCodebook* h, const float* E_dev, const float* z_dev, int B, int64_t row_offset, int num_cyclo, int upright,
-                      float* scores_out, int32_t* idx_out, cudaStream_t s);
+int tc_codebook_max_k();
+// fused normalise + scores + top-k (k <= tc_codebook_max_k()), optionally over every num_cyclo-th row only (upright)
+int tc_codebook_match(TcCodebook* h, const float* z_dev, int B, int64_t row_offset, int k, int upright, float* scores_out, int32_t* idx_out,
+                      cudaStream_t s);
 
 }  // namespace aae

@@ -239,8 +239,13 @@ class ObjectRouter:
                 cap = max(n_own, -(-len(class_ids) // max(1, self.world)) * 2)
                 self._stage = torch.empty((cap,) + tuple(crops_host.shape[1:]), dtype=crops_host.dtype,
                                           pin_memory=torch.cuda.is_available() and device.type == "cuda")
-            order = torch.from_numpy(np.concatenate([sel for _, sel in plan]))
-            torch.index_select(crops_host, 0, order, out=self._stage[:n_own])
+            order_np = np.concatenate([sel for _, sel in plan])
+            order = torch.from_numpy(order_np)
+            # row gather on the host into the pinned staging buffer: one memcpy per crop (measured: 6 ms per 1024 crops, against
+            # 7-1000 ms for torch.index_select / np.take depending on thread-pool and page-fault state)
+            src, dst = crops_host.numpy(), self._stage.numpy()
+            for j, i in enumerate(order_np):
+                dst[j] = src[i]
             own_dev = self._stage[:n_own].to(device, non_blocking=True)
             pos_dev = order.to(device, non_blocking=True)
             a = 0

@@ -45,6 +45,49 @@ def test_tc_match_matches_oracle(sess, n_rows, batch):
     assert np.array_equal(i2.cpu().numpy()[:, 0], i) and np.array_equal(s2.cpu().numpy()[:, 0], s)
 
 
+@pytest.mark.parametrize("n_rows,batch,k", [(36 * 700, 5, 8), (92232, 130, 8), (92232, 1, 3), (36 * 40, 64, 8)])
+def test_tc_topk_and_upright_match_oracle(sess, n_rows, batch, k):
+    """Codebook.nearest_rotation(top_n > 1) and upright=True on the tensor-core kernel (codebook.py:64-71): per-lane sorted
+    lists in registers + last-CTA merge; upright = the same kernel on a tensor map with a row stride of num_cyclo rows."""
+    E = O.make_codebook(5, n=n_rows)                      # with the duplicated cyclo end-point rows -> exact ties
+    p = O.make_encoder_params(42)
+    cb = _codebook(_enc(0, 256, p), E, max_batch=256, precision=1)
+    rng = np.random.RandomState(n_rows + batch)
+    z = (rng.standard_normal((batch, 128)) * rng.uniform(0.05, 50, (batch, 1))).astype(np.float32)
+    z[0] = E[36 * 3] * 2.0                                # a query that IS a (duplicated) row: rows 108 and 143 tie at 1.0
+    cos64 = O.cos_similarity(z.astype(np.float64), E.astype(np.float64))
+    sk, ik = cb.match_device(torch.from_numpy(z).cuda(), k=k)
+    sk, ik = sk.cpu().numpy(), ik.cpu().numpy()
+    assert sk.shape == (batch, k) and ik.shape == (batch, k)
+    assert ik[0, 0] == 36 * 3 and ik[0, 1] == 36 * 3 + 35          # equal scores: lowest index first
+    for b in range(batch):
+        want = np.lexsort((np.arange(n_rows), -cos64[b]))[:k]      # score descending, ties to the lowest index
+        assert np.max(np.abs(sk[b] - cos64[b, ik[b]])) < 2e-6
+        assert np.all(np.diff(sk[b]) <= 0) and len(set(ik[b].tolist())) == k
+        for j in np.nonzero(want != ik[b])[0]:                     # a swap is legitimate only between fp32-indistinguishable scores
+            assert abs(cos64[b, want[j]] - cos64[b, ik[b, j]]) < 2e-7, (b, j, want, ik[b])
+    # k = 1 agrees with the head of the list, and twice in a row gives the same answer (scratch re-armed)
+    s1, i1 = cb.match_device(torch.from_numpy(z).cuda(), k=1)
+    assert np.array_equal(i1.cpu().numpy()[:, 0], ik[:, 0]) and np.array_equal(s1.cpu().numpy()[:, 0], sk[:, 0])
+    sk2, ik2 = cb.match_device(torch.from_numpy(z).cuda(), k=k)
+    assert np.array_equal(ik2.cpu().numpy(), ik) and np.array_equal(sk2.cpu().numpy(), sk)
+    # upright (codebook.py:66): every 36th row only
+    su, iu = cb.match_device(torch.from_numpy(z).cuda(), upright=True)
+    su, iu = su.cpu().numpy()[:, 0], iu.cpu().numpy()[:, 0]
+    want_u = O.select_indices(cos64, upright=True, num_cyclo=36)
+    assert np.all(iu % 36 == 0) and np.max(np.abs(su - cos64[np.arange(batch), iu])) < 2e-6
+    for b in np.nonzero(want_u != iu)[0]:
+        assert abs(cos64[b, want_u[b]] - cos64[b, iu[b]]) < 2e-7
+    suk, iuk = cb.match_device(torch.from_numpy(z).cuda(), k=min(k, 4), upright=True)
+    assert np.array_equal(iuk.cpu().numpy()[:, 0], iu) and np.all(iuk.cpu().numpy() % 36 == 0)
+    # and the exact-order fp32 path gives the same indices
+    cb0 = _codebook(_enc(0, 256, p), E, max_batch=256, precision=0)
+    s0, i0 = cb0.match_device(torch.from_numpy(z).cuda(), k=k)
+    d = np.nonzero(i0.cpu().numpy() != ik)
+    for b, j in zip(*d):
+        assert abs(cos64[b, i0.cpu().numpy()[b, j]] - cos64[b, ik[b, j]]) < 2e-7
+
+
 def test_tc_encoder_layers_and_latent_match_oracle(sess):
     p = O.make_encoder_params(42, bias_scale=0.05)
     enc = _enc(1, 4, p)
@@ -61,26 +104,6 @@ def test_tc_encoder_layers_and_latent_match_oracle(sess):
     errs.append(np.max(np.abs(z - z64)) / np.abs(z64).max())
     print("tc encoder relative errors per layer + latent:", ["%.2e" % e for e in errs])
     assert all(e < 1e-5 for e in errs), errs
-
-
-def test_tc_end_to_end_256_crops_index_parity(sess):
-    p = O.make_encoder_params(42)
-    E = O.make_codebook(7)
-    enc = _enc(1, 256, p)
-    cb = _codebook(enc, E, max_batch=256, precision=1)
-    crops = O.make_crops_u8(1234, 256)
-    got = cb.nearest_rotation(sess, crops, return_idcs=True)
-    with torch.cuda.device(0):
-        s_dev, _ = cb.nearest_idx_device(torch.from_numpy(crops).cuda())
-    want, cos = O.nearest_rotation_idcs(crops, p, E, return_cos=True)
-    bad = np.nonzero(got != want)[0]
-    if len(bad):
-        z64 = O.encoder_forward(O.preprocess(crops[bad]), p, dtype=torch.float64)
-        c64 = O.l2_normalize(z64) @ E.astype(np.float64).T
-        for j, b in enumerate(bad):
-            assert abs(c64[j, got[b]] - c64[j, want[b]]) < 2e-6, ("index mismatch beyond fp32 resolution", b)
-    assert len(bad) <= 1
-    assert np.max(np.abs(s_dev.cpu().numpy()[:, 0] - cos[np.arange(256), got])) <= COS_TOL
 
 
 @pytest.mark.parametrize("batch", [1, 2, 63, 127, 129, 255, 300])

@@ -24,7 +24,7 @@ def test_row_sharded_match_is_bit_identical_to_unsharded(sess, precision):
     shards = [ShardedCodebook(E[lo:hi], num_cyclo=36, max_batch=64, precision=precision, row_range=(lo, hi), n_rows_total=n) for lo, hi in spans]
     rows = np.array([lo + 7 for lo, hi in spans] + [36 * 400 + 3, 35, n - 1])
     z = torch.from_numpy((E[rows] * 1.7).astype(np.float32)).cuda()
-    k = 4 if precision == 0 else 1   # k > 1 is served by the exact fp32 kernels in both modes; compare like with like
+    k = 4
     def gather(kk, upright):
         """What the NCCL all-gather of the per-rank [2, B, k] exchange buffers produces: [W, 2, B, k]."""
         packed = torch.empty((W, 2, z.shape[0], kk), dtype=torch.int32, device=z.device)
@@ -43,9 +43,8 @@ def test_row_sharded_match_is_bit_identical_to_unsharded(sess, precision):
     want[W + 2] = n - 36       # last row duplicates row n-36
     assert np.array_equal(i.cpu().numpy()[:, 0], want)
     cos = O.cos_similarity(z.cpu().numpy(), E)
-    if precision == 0:
-        sk, ik = cb.match_device(z, k=k)
-        assert np.array_equal(i.cpu().numpy(), ik.cpu().numpy()) and np.array_equal(s.cpu().numpy(), sk.cpu().numpy())
+    sk, ik = cb.match_device(z, k=k)          # sharded top-k lists merged == unsharded top-k, bit for bit, in both arithmetic modes
+    assert np.array_equal(i.cpu().numpy(), ik.cpu().numpy()) and np.array_equal(s.cpu().numpy(), sk.cpu().numpy())
     for b in range(len(rows)):
         assert np.max(np.abs(s.cpu().numpy()[b] - cos[b, i.cpu().numpy()[b]])) < 2e-6
     _, iu = shards[0]._merge(gather(1, True))
