@@ -36,6 +36,8 @@ _SIGS = {
     "aae_encoder_get_weights": (_I, [_P, _I, _P, _P, _P]),
     "aae_encoder_forward_u8": (_I, [_P, _P, _I, _P, _P]),
     "aae_encoder_forward_f32": (_I, [_P, _P, _I, _P, _P]),
+    "aae_encoder_range_status": (_I, [_P, _P]),
+    "aae_encoder_range_word": (_I, [_P, C.POINTER(_P)]),
     "aae_encoder_activation": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_L)]),
     "aae_encoder_profile": (_I, [_P, _I, _P, _I]),
     "aae_codebook_profile": (_I, [_P, _I, _P, _I]),
@@ -52,6 +54,7 @@ _SIGS = {
     "aae_decoder_set_weights": (_I, [_P, _I, _P, _P, _P]),
     "aae_decoder_get_weights": (_I, [_P, _I, _P, _P, _P]),
     "aae_decoder_forward": (_I, [_P, _P, _I, _P, _P]),
+    "aae_decoder_range_status": (_I, [_P, _P]),
     "aae_bootstrap_l2_loss": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "aae_trainer_create": (_I, [_P, _P, _I, _F, _F, _F, _F, C.POINTER(_P)]),
     "aae_trainer_destroy": (_I, [_P]),

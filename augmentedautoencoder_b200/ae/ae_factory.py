@@ -151,6 +151,9 @@ class TrainOp(Tensor):
 
     def _run(self, ctx):
         x, y = self._io(ctx)
+        for m in (self._ae._encoder, self._ae._decoder):
+            if m not in ctx.touched:
+                ctx.touched.append(m)
         return self.step_device(x, y, update=True)
 
     def gradients(self, device):

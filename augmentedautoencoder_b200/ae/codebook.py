@@ -123,6 +123,7 @@ class Codebook(object):
         with torch.cuda.device(session.device):
             _, idx = self.nearest_idx_device(xd, k=top_n, upright=upright)
         idx = idx.cpu().numpy().astype(np.int64)
+        self._encoder.check_range(session.device)      # synchronised by the copy above: out-of-range activations raise instead of passing as indices
         if top_n == 1:
             idcs = idx[:, 0]
         else:
@@ -157,9 +158,15 @@ class Codebook(object):
             _, idx = self.nearest_idx_device(xd.contiguous(), k=1, upright=upright)
             host = self._pinned_result(idx.shape)
             host.copy_(idx, non_blocking=True)
+            # the range guard's word rides behind the indices on the same stream: no extra synchronisation in the pipeline
+            word = self._encoder.range_word(dev)
+            flag = None
+            if word is not None:
+                flag = self._pinned_result((1,))
+                flag.copy_(word, non_blocking=True)
             done = torch.cuda.Event()
             done.record(compute)
-        return PendingIndices(host, done)
+        return PendingIndices(host, done, flag, lambda: self._encoder.check_range(dev))
 
     def _pinned_result(self, shape, depth=8):
         """Ring of pinned host buffers for the async read-back (cudaHostAlloc per call would cost more than the kernel)."""
@@ -236,14 +243,16 @@ class Codebook(object):
 class PendingIndices:
     """Handle returned by Codebook.nearest_rotation_async."""
 
-    def __init__(self, host_buf, event):
-        self._host, self._event = host_buf, event
+    def __init__(self, host_buf, event, flag=None, check=None):
+        self._host, self._event, self._flag, self._check = host_buf, event, flag, check
 
     def done(self):
         return self._event.query()
 
     def result(self):
         self._event.synchronize()
+        if self._flag is not None and int(self._flag[0]) != 0:
+            self._check()              # synchronises, clears the guard and raises AaeError naming the layers
         return self._host.numpy().astype(np.int64)[:, 0]   # astype copies: the pinned buffer goes back to the ring
 
 

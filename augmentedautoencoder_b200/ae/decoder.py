@@ -24,6 +24,7 @@ class Decoder(_DeviceModule):
         L = _lib.lib()
         self._create, self._destroy = L.aae_decoder_create, L.aae_decoder_destroy
         self._set, self._get = L.aae_decoder_set_weights, L.aae_decoder_get_weights
+        self._range_status = L.aae_decoder_range_status
         self._reconstruction_target = reconstruction_target
         self._latent_code = latent_code
         self._auxiliary_mask = auxiliary_mask
@@ -76,8 +77,11 @@ class Decoder(_DeviceModule):
 
     @lazy_property
     def x(self):
-        return Tensor("conv2d_out/Sigmoid", (None,) + self._out_shape, np.float32,
-                      lambda ctx: self.decode_device(ctx.get(self._latent_code)))
+        def fn(ctx):
+            if self not in ctx.touched:
+                ctx.touched.append(self)
+            return self.decode_device(ctx.get(self._latent_code))
+        return Tensor("conv2d_out/Sigmoid", (None,) + self._out_shape, np.float32, fn)
 
     @staticmethod
     def loss_device(x_dev, target_dev, bootstrap_ratio, with_grad=False):

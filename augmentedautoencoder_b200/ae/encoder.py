@@ -32,8 +32,8 @@ class _RawCudaArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-def tensor_from_ptr(ptr, shape, device):
-    return torch.as_tensor(_RawCudaArray(ptr, shape), device=device)
+def tensor_from_ptr(ptr, shape, device, typestr="<f4"):
+    return torch.as_tensor(_RawCudaArray(ptr, shape, typestr), device=device)
 
 
 class _DeviceModule:
@@ -112,9 +112,24 @@ class _DeviceModule:
                 cfg = _lib.make_cfg(*self._cfg_args)
                 st = self._create(dev, C.byref(cfg), C.byref(h))
             _lib.check(st, type(self).__name__ + " create")
+            try:
+                self._upload(dev, h)
+            except Exception:          # e.g. a weight outside the tensor-core range: no half-initialised handle may stay behind
+                self._destroy(h)
+                raise
             self._handles[dev] = h
-            self._upload(dev, h)
         return self._handles[dev]
+
+    def check_range(self, device=None):
+        """Raises AaeError if a forward / training step launched so far on this module left the range of the split-fp16
+        tensor-core arithmetic (|activation| >= 4094; include/aae_b200.h: aae_*_range_status).  Synchronises the current
+        stream, so the asynchronous device entry points (encode_device / decode_device) do not call it; every path that
+        hands results to the host does."""
+        for dev, h in self._handles.items():
+            if device is not None and dev != (device.index if isinstance(device, torch.device) else int(device)):
+                continue
+            with torch.cuda.device(dev):
+                _lib.check(self._range_status(h, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), type(self).__name__ + " range check")
 
     def set_precision(self, precision):
         """Re-create the device handles with another aae_precision (weights are kept; device-side values are read back first)."""
@@ -150,6 +165,7 @@ class Encoder(_DeviceModule):
         L = _lib.lib()
         self._create, self._destroy = L.aae_encoder_create, L.aae_encoder_destroy
         self._set, self._get = L.aae_encoder_set_weights, L.aae_encoder_get_weights
+        self._range_status = L.aae_encoder_range_status
         self._input = input
         self._latent_space_size = int(latent_space_size)
         self._num_filters = list(num_filters)
@@ -206,10 +222,19 @@ class Encoder(_DeviceModule):
         return out
 
     def _eval_input(self, ctx):
+        if self not in ctx.touched:
+            ctx.touched.append(self)
         x = to_device_input(ctx.get(self._input), ctx.session.device)
         if x.ndim == 3:
             x = x.unsqueeze(0)
         return x
+
+    def range_word(self, device):
+        """The range guard's device word as an int32 tensor view (None on the fp32 path): see aae_encoder_range_word."""
+        h = self.handle(device)
+        p = C.c_void_p()
+        _lib.check(_lib.lib().aae_encoder_range_word(h, C.byref(p)), "range word")
+        return tensor_from_ptr(p.value, (1,), device, typestr="<i4") if p.value else None
 
     @lazy_property
     def z(self):

@@ -89,6 +89,7 @@ class RunContext:
         self.session = session
         self.feeds = feeds
         self.memo = {}
+        self.touched = []     # device modules whose kernels ran in this call (their range guard is checked by Session.run)
 
     def get(self, tensor):
         key = id(tensor)
@@ -134,24 +135,29 @@ class Session:
             feeds[id(k)] = v
         return feeds
 
-    def run_device(self, fetches, feed_dict=None):
+    def _evaluate(self, fetches, feed_dict):
         ctx = RunContext(self, self._bind(feed_dict))
         with torch.cuda.device(self.device):
             if isinstance(fetches, (list, tuple)):
-                return [ctx.get(f) for f in fetches]
-            return ctx.get(fetches)
+                return [ctx.get(f) for f in fetches], ctx
+            return ctx.get(fetches), ctx
+
+    def run_device(self, fetches, feed_dict=None):
+        """Asynchronous: torch CUDA tensors, no host synchronisation (and therefore no range-guard check: Encoder.check_range)."""
+        return self._evaluate(fetches, feed_dict)[0]
 
     def run(self, fetches, feed_dict=None):
-        out = self.run_device(fetches, feed_dict)
+        out, ctx = self._evaluate(fetches, feed_dict)
 
         def host(v):
             if isinstance(v, torch.Tensor):
                 return v.detach().cpu().numpy()
             return v
 
-        if isinstance(fetches, (list, tuple)):
-            return [host(v) for v in out]
-        return host(out)
+        res = [host(v) for v in out] if isinstance(fetches, (list, tuple)) else host(out)
+        for m in ctx.touched:               # results are on the host now: a value outside the tensor-core range must not pass silently
+            m.check_range(self.device)
+        return res
 
     def close(self):
         pass

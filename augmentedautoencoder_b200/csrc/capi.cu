@@ -170,6 +170,27 @@ int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   return AAE_OK;
 }
 
+// Run-time range guard of the tensor-core path's static fp16 scaling: kernels set bits in a device word
+// instead of producing inf silently.  `peek` reads the word (the caller has synchronised the stream the work ran on), names
+// the offending layers in the error string, clears it and returns AAE_ERR_UNSUPPORTED; 0 bits -> AAE_OK.
+int range_peek(unsigned* flag_dev, const char* what, int act_layer_base, cudaStream_t s) {
+  if (!flag_dev) return AAE_OK;
+  unsigned bits = 0;
+  AAE_CUDA_OK(cudaMemcpyAsync(&bits, flag_dev, sizeof(bits), cudaMemcpyDeviceToHost, s));
+  AAE_CUDA_OK(cudaStreamSynchronize(s));
+  if (bits == 0) return AAE_OK;
+  AAE_CUDA_OK(cudaMemsetAsync(flag_dev, 0, sizeof(bits), s));
+  char acts[128] = "", wts[128] = "";
+  for (int l = 0; l < 15; ++l) {
+    if (bits & (1u << l)) snprintf(acts + strlen(acts), sizeof(acts) - strlen(acts), " %d", l + act_layer_base);
+    if (bits & (1u << (16 + l))) snprintf(wts + strlen(wts), sizeof(wts) - strlen(wts), " %d", l);
+  }
+  set_error("%s: values outside the range of the split-fp16 tensor-core arithmetic (AAE_PREC_TC_SPLIT)%s%s%s%s%s -- use AAE_PREC_FP32_SIMT for "
+            "this model", what, acts[0] ? "; |activation| >= 4094 written by layer(s)" : "", acts, wts[0] ? "; |weight| >= 255.9 in layer(s)" : "", wts,
+            (bits & (1u << 15)) ? "; |latent| >= 4094 at the decoder input" : "");
+  return AAE_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 }  // namespace aae
 
@@ -354,7 +375,20 @@ extern "C" int aae_encoder_set_weights(aae_encoder* h, int layer, const float* k
   if (h->tc && kernel_any) AAE_TRY(tc_encoder_pack_weights(h->tc, layer, w.p, s));
   if (h->tc) AAE_TRY(tc_encoder_set_bias(h->tc, layer, b.p));
   AAE_CUDA_OK(cudaStreamSynchronize(s));  // host source buffers may be freed by the caller on return
+  if (h->tc) AAE_TRY(range_peek(tc_encoder_range_flag(h->tc), "encoder set_weights", 0, s));
   return AAE_OK;
+}
+
+extern "C" int aae_encoder_range_word(aae_encoder* h, const uint32_t** word_dev) {
+  AAE_REQUIRE(h != nullptr && word_dev != nullptr, "null argument");
+  *word_dev = h->tc ? tc_encoder_range_flag(h->tc) : nullptr;
+  return AAE_OK;
+}
+
+extern "C" int aae_encoder_range_status(aae_encoder* h, void* stream) {
+  AAE_REQUIRE(h != nullptr, "encoder handle is null");
+  DeviceGuard g(h->device);
+  return h->tc ? range_peek(tc_encoder_range_flag(h->tc), "encoder", 0, (cudaStream_t)stream) : AAE_OK;
 }
 
 extern "C" int aae_encoder_get_weights(aae_encoder* h, int layer, float* kernel_any, float* bias_any, void* stream) {
@@ -660,7 +694,14 @@ extern "C" int aae_decoder_set_weights(aae_decoder* h, int layer, const float* k
   h->w_version += 1;
   if (h->tc) AAE_TRY(tc_decoder_pack_weights(h->tc, layer, kernel_any ? w.p : nullptr, bias_any ? b.p : nullptr, s));
   AAE_CUDA_OK(cudaStreamSynchronize(s));
+  if (h->tc) AAE_TRY(range_peek(tc_decoder_range_flag(h->tc), "decoder set_weights", 0, s));
   return AAE_OK;
+}
+
+extern "C" int aae_decoder_range_status(aae_decoder* h, void* stream) {
+  AAE_REQUIRE(h != nullptr, "decoder handle is null");
+  DeviceGuard g(h->device);
+  return h->tc ? range_peek(tc_decoder_range_flag(h->tc), "decoder", 0, (cudaStream_t)stream) : AAE_OK;
 }
 
 extern "C" int aae_decoder_get_weights(aae_decoder* h, int layer, float* kernel_any, float* bias_any, void* stream) {

@@ -11,9 +11,9 @@ struct TcConv1;
 bool tc_conv1_supported(const aae_net_cfg* cfg);
 int tc_conv1_create(int device, const aae_net_cfg* cfg, TcConv1** out);
 void tc_conv1_destroy(TcConv1* h);
-int tc_conv1_pack(TcConv1* h, const float* w_dev, int K, float w_scale, cudaStream_t s);
+int tc_conv1_pack(TcConv1* h, const float* w_dev, int K, float w_scale, unsigned* range_flag, unsigned range_bit, cudaStream_t s);
 int tc_conv1_forward(TcConv1* h, const aae_net_cfg* cfg, const void* crops, int src_u8, int B, const float* bias, float act_scale,
-                     float w_scale, __half* out_hi, __half* out_lo, cudaStream_t s);
+                     float w_scale, __half* out_hi, __half* out_lo, unsigned* range_flag, cudaStream_t s);
 
 int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out);
 void tc_encoder_destroy(TcEncoder* h);
@@ -23,6 +23,8 @@ int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const
                        float* z_out, cudaStream_t s);
 
 int tc_encoder_set_bias(TcEncoder* h, int layer, const float* bias_dev);
+// device word of the run-time range guard (tc_plan.cuh): bit l = activation of layer l overflowed fp16, bit 16 + l = a weight did
+unsigned* tc_encoder_range_flag(TcEncoder* h);
 int tc_encoder_activation(TcEncoder* h, int layer, int B, const float** ptr, int64_t* count, cudaStream_t s);
 void tc_encoder_enable_timer(TcEncoder* h, bool on);
 int tc_encoder_read_timer(TcEncoder* h, float* ms, int cap);
@@ -32,6 +34,7 @@ int tc_decoder_create(int device, const aae_net_cfg* cfg, TcDecoder** out);
 void tc_decoder_destroy(TcDecoder* h);
 int tc_decoder_pack_weights(TcDecoder* h, int layer, const float* w_dev, const float* b_dev, cudaStream_t s);
 int tc_decoder_forward(TcDecoder* h, const float* z_dev, int B, float* x_out, cudaStream_t s);
+unsigned* tc_decoder_range_flag(TcDecoder* h);
 const float* tc_decoder_merged_weights(const TcDecoder* h);   // fp32 merged sub-pixel weights of the layer packed last
 
 // ---- training: backward GEMMs (tc_train.cu); units are the conv layers in backward order (decoder L..1, encoder L..2)

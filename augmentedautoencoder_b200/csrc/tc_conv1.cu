@@ -44,6 +44,7 @@ struct Conv1Params {
   float unscale, out_scale, in_scale;
   __half* out_hi;
   __half* out_lo;
+  unsigned* range_flag;    // run-time range guard (tc_plan.cuh): bit 0 = this layer's activation overflowed fp16 at out_scale
 };
 
 template <int N>
@@ -233,12 +234,15 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + c * 32), v);
         tmem_ld_wait();
         uint32_t hi[16], lo[16];
+        float amax = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const float a = fmaxf(__uint_as_float(v[j]) * p.unscale + bias_s[c * 32 + j], 0.f) * p.out_scale;
           const float bb = fmaxf(__uint_as_float(v[j + 1]) * p.unscale + bias_s[c * 32 + j + 1], 0.f) * p.out_scale;
+          amax = fmaxf(amax, fmaxf(a, bb));
           split_f16x2(a, bb, hi[j >> 1], lo[j >> 1]);
         }
+        if (p.range_flag != nullptr && !(amax < 65520.f)) atomicOr(p.range_flag, 1u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           *reinterpret_cast<uint4*>(my_hi + c * 64 + j * 16) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
@@ -303,11 +307,13 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
 }
 
 // W fp32 [75][N] (HWIO flattened) -> (hi, lo) fp16 [N][128] K-major, scaled, zero for k >= K
-__global__ void pack_conv1_weights_kernel(const float* __restrict__ w, int K, int N, float scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+__global__ void pack_conv1_weights_kernel(const float* __restrict__ w, int K, int N, float scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                                          unsigned* __restrict__ range_flag, unsigned range_bit) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * 128) return;
   const int n = i / 128, k = i - n * 128;
   const float v = k < K ? w[(long long)k * N + n] * scale : 0.f;
+  if (range_flag != nullptr && !(fabsf(v) < 65520.f)) atomicOr(range_flag, range_bit);
   __half h, l;
   split_f16(v, h, l);
   hi[i] = h;
@@ -354,15 +360,16 @@ void tc_conv1_destroy(TcConv1* h) {
   delete h;
 }
 
-int tc_conv1_pack(TcConv1* h, const float* w_dev, int K, float w_scale, cudaStream_t s) {
-  pack_conv1_weights_kernel<<<(unsigned)ceil_div(h->N * 128, 256), 256, 0, s>>>(w_dev, K, h->N, w_scale, h->w_hi, h->w_lo);
+int tc_conv1_pack(TcConv1* h, const float* w_dev, int K, float w_scale, unsigned* range_flag, unsigned range_bit, cudaStream_t s) {
+  pack_conv1_weights_kernel<<<(unsigned)ceil_div(h->N * 128, 256), 256, 0, s>>>(w_dev, K, h->N, w_scale, h->w_hi, h->w_lo, range_flag, range_bit);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }
 
 int tc_conv1_forward(TcConv1* h, const aae_net_cfg* cfg, const void* crops, int src_u8, int B, const float* bias, float act_scale,
-                     float w_scale, __half* out_hi, __half* out_lo, cudaStream_t s) {
+                     float w_scale, __half* out_hi, __half* out_lo, unsigned* range_flag, cudaStream_t s) {
   Conv1Params p;
+  p.range_flag = range_flag;
   p.x = crops; p.B = B; p.H = cfg->in_h; p.W = cfg->in_w; p.C = cfg->in_c;
   p.OH = cfg->in_h / 2; p.OW = cfg->in_w / 2; p.N = h->N;
   p.pad_t = std::max((p.OH - 1) * 2 + 5 - p.H, 0) / 2;

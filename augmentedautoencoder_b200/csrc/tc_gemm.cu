@@ -599,7 +599,7 @@ namespace {
 
 // W fp32 [taps][Cin][Cout] (HWIO flattened) -> Wp_{hi,lo} fp16 [Cout][taps*Cin], value scaled by `scale`
 __global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, float scale, __half* __restrict__ hi,
-                                    __half* __restrict__ lo) {
+                                    __half* __restrict__ lo, unsigned* __restrict__ range_flag, unsigned range_bit) {
   __shared__ float tile[32][33];
   const int tap = blockIdx.z;
   const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
@@ -612,7 +612,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int c
     const int co = co0 + i, ci = ci0 + threadIdx.x;
     if (co < cout && ci < cin) {
       __half h, l;
-      split_f16(tile[threadIdx.x][i] * scale, h, l);
+      const float v = tile[threadIdx.x][i] * scale;
+      if (range_flag != nullptr && !(fabsf(v) < TC_F16_OVERFLOW)) atomicOr(range_flag, range_bit);
+      split_f16(v, h, l);
       const long long o = (long long)co * taps * cin + (long long)tap * cin + ci;
       hi[o] = h;
       lo[o] = l;
@@ -833,6 +835,12 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
     st = dev_alloc((void**)&h->partials, (size_t)h->dense_splits * (B + 128) * cfg->latent * sizeof(float));
     D.gp.out_f32 = h->partials;
   }
+  if (st == AAE_OK) st = dev_alloc((void**)&h->range_flag, sizeof(unsigned));
+  if (st == AAE_OK)
+    for (size_t i = 0; i + 1 < h->layers.size(); ++i) {   // layers[i] writes the activation of conv layer i + 1 (0-based); the dense layer writes fp32
+      h->layers[i].gp.range_flag = h->range_flag;
+      h->layers[i].gp.range_bit = 1u << (i + 1);
+    }
   if (st == AAE_OK && tc_conv1_supported(cfg)) st = tc_conv1_create(device, cfg, &h->conv1);
   if (st != AAE_OK) { tc_encoder_destroy(h); return st; }
   *out = h;
@@ -844,6 +852,7 @@ void tc_encoder_destroy(TcEncoder* h) {
   for (auto& T : h->layers) { cudaFree(T.in_hi); cudaFree(T.in_lo); cudaFree(T.w_hi); cudaFree(T.w_lo); }
   cudaFree(h->partials);
   cudaFree(h->dbg);
+  cudaFree(h->range_flag);
   tc_conv1_destroy(h->conv1);
   for (auto e : h->ev) cudaEventDestroy(e);
   delete h;
@@ -851,16 +860,19 @@ void tc_encoder_destroy(TcEncoder* h) {
 
 int tc_encoder_pack_weights(TcEncoder* h, int layer, const float* w_dev, cudaStream_t s) {
   if (layer == 0) {
-    if (h->conv1) return tc_conv1_pack(h->conv1, w_dev, h->cfg.kernel_size * h->cfg.kernel_size * h->cfg.in_c, W_SCALE, s);
+    if (h->conv1) return tc_conv1_pack(h->conv1, w_dev, h->cfg.kernel_size * h->cfg.kernel_size * h->cfg.in_c, W_SCALE, h->range_flag, 1u << 16, s);
     return AAE_OK;  // conv1 on the fp32 SIMT kernel
   }
   AAE_REQUIRE(layer >= 1 && layer <= (int)h->layers.size(), "tc pack: layer %d out of range", layer);
   TcLayer& T = h->layers[layer - 1];
   dim3 grid((unsigned)ceil_div(T.out_c, 32), (unsigned)ceil_div(T.in_c, 32), (unsigned)T.taps), block(32, 8);
-  pack_weights_kernel<<<grid, block, 0, s>>>(w_dev, T.taps, T.in_c, T.out_c, W_SCALE, T.w_hi, T.w_lo);
+  pack_weights_kernel<<<grid, block, 0, s>>>(w_dev, T.taps, T.in_c, T.out_c, W_SCALE, T.w_hi, T.w_lo, h->range_flag, 1u << (16 + layer));
   AAE_LAUNCH_OK();
   return AAE_OK;
 }
+
+unsigned* tc_encoder_range_flag(TcEncoder* h) { return h->range_flag; }
+unsigned* tc_decoder_range_flag(TcDecoder* h) { return h->range_flag; }
 
 void tc_encoder_enable_timer(TcEncoder* h, bool on) { h->timer_on = on; }
 
@@ -885,7 +897,7 @@ int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const
   h->ev_used = 0;
   tc_mark(h, s);
   if (h->conv1) {
-    AAE_TRY(tc_conv1_forward(h->conv1, &cfg, crops, src_u8, B, b0, ACT_SCALE, W_SCALE, h->layers[0].in_hi, h->layers[0].in_lo, s));
+    AAE_TRY(tc_conv1_forward(h->conv1, &cfg, crops, src_u8, B, b0, ACT_SCALE, W_SCALE, h->layers[0].in_hi, h->layers[0].in_lo, h->range_flag, s));
   } else {  // conv1 (Cin = 3, K = 75): fp32 SIMT implicit GEMM, epilogue writes conv2's space-to-depth (hi, lo) input directly
     IGemmParams p;
     memset(&p, 0, sizeof(p));
@@ -951,9 +963,11 @@ int tc_encoder_activation(TcEncoder* h, int layer, int B, const float** ptr, int
 // (depth-to-space).  The output layer (Cout = 3 -> N = 12, padded to 32) applies the sigmoid and writes fp32 NHWC.
 namespace {
 
-__global__ void split_scale_kernel(const float* __restrict__ x, long long n, float scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+__global__ void split_scale_kernel(const float* __restrict__ x, long long n, float scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                                   unsigned* __restrict__ range_flag, unsigned range_bit) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     __half h, l;
+    if (range_flag != nullptr && !(fabsf(x[i] * scale) < TC_F16_OVERFLOW)) atomicOr(range_flag, range_bit);
     split_f16(x[i] * scale, h, l);
     hi[i] = h;
     lo[i] = l;
@@ -961,12 +975,14 @@ __global__ void split_scale_kernel(const float* __restrict__ x, long long n, flo
 }
 
 // merged weights Wm [9][cin][n4] -> operand of the tap-separable output layer: row (tap * n4 + m) = Wm[tap][:, m], rows >= 9*n4 zero
-__global__ void pack_out_sep_kernel(const float* __restrict__ wm, int cin, int n4, float scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+__global__ void pack_out_sep_kernel(const float* __restrict__ wm, int cin, int n4, float scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                                    unsigned* __restrict__ range_flag, unsigned range_bit) {
   const int total = 128 * cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ci = i % cin, n = i / cin;
     const int tap = n / n4, m = n - tap * n4;
     const float v = tap < 9 ? wm[((long long)tap * cin + ci) * n4 + m] * scale : 0.f;
+    if (range_flag != nullptr && !(fabsf(v) < TC_F16_OVERFLOW)) atomicOr(range_flag, range_bit);
     __half a, d;
     split_f16(v, a, d);
     hi[i] = a;
@@ -1109,10 +1125,13 @@ int tc_decoder_create(int device, const aae_net_cfg* cfg, TcDecoder** out) {
     h->wm_floats = std::max(h->wm_floats, (size_t)9 * T.in_c * 4 * T.out_c);
   }
   if (st == AAE_OK) st = dev_alloc((void**)&h->wm_tmp, h->wm_floats * sizeof(float));
+  if (st == AAE_OK) st = dev_alloc((void**)&h->range_flag, sizeof(unsigned));
   if (st == AAE_OK) {
     for (size_t i = 0; i + 1 < h->layers.size(); ++i) {
       h->layers[i].gp.out_hi = h->layers[i + 1].in_hi;
       h->layers[i].gp.out_lo = h->layers[i + 1].in_lo;
+      h->layers[i].gp.range_flag = h->range_flag;       // bit i: the activation written by layer i (0 = dense_1)
+      h->layers[i].gp.range_bit = 1u << i;
     }
   }
   if (st != AAE_OK) { tc_decoder_destroy(h); return st; }
@@ -1126,6 +1145,7 @@ void tc_decoder_destroy(TcDecoder* h) {
   for (auto b : h->bias_dev) cudaFree(b);
   cudaFree(h->wm_tmp);
   cudaFree(h->out_p);
+  cudaFree(h->range_flag);
   delete h;
 }
 
@@ -1137,7 +1157,7 @@ int tc_decoder_pack_weights(TcDecoder* h, int layer, const float* w_dev, const f
   if (layer == 0) {
     if (w_dev) {
       dim3 grid((unsigned)ceil_div(T.out_c, 32), (unsigned)ceil_div(T.in_c, 32), 1);
-      pack_weights_kernel<<<grid, block, 0, s>>>(w_dev, 1, T.in_c, T.out_c, W_SCALE, T.w_hi, T.w_lo);
+      pack_weights_kernel<<<grid, block, 0, s>>>(w_dev, 1, T.in_c, T.out_c, W_SCALE, T.w_hi, T.w_lo, h->range_flag, 1u << 16);
       AAE_LAUNCH_OK();
     }
     if (b_dev) T.gp.bias = b_dev;      // device pointer owned by the decoder handle
@@ -1147,10 +1167,10 @@ int tc_decoder_pack_weights(TcDecoder* h, int layer, const float* w_dev, const f
   if (w_dev) {
     AAE_TRY(launch_merge_subpixel_weights(w_dev, T.in_c, T.out_c, h->wm_tmp, s));
     if (sep) {
-      pack_out_sep_kernel<<<64, 256, 0, s>>>(h->wm_tmp, T.in_c, 4 * T.out_c, W_SCALE, T.w_hi, T.w_lo);
+      pack_out_sep_kernel<<<64, 256, 0, s>>>(h->wm_tmp, T.in_c, 4 * T.out_c, W_SCALE, T.w_hi, T.w_lo, h->range_flag, 1u << (16 + layer));
     } else {
       dim3 grid((unsigned)ceil_div(4 * T.out_c, 32), (unsigned)ceil_div(T.in_c, 32), 9);
-      pack_weights_kernel<<<grid, block, 0, s>>>(h->wm_tmp, 9, T.in_c, 4 * T.out_c, W_SCALE, T.w_hi, T.w_lo);
+      pack_weights_kernel<<<grid, block, 0, s>>>(h->wm_tmp, 9, T.in_c, 4 * T.out_c, W_SCALE, T.w_hi, T.w_lo, h->range_flag, 1u << (16 + layer));
     }
     AAE_LAUNCH_OK();
   }
@@ -1172,7 +1192,7 @@ const float* tc_decoder_merged_weights(const TcDecoder* h) { return h->wm_tmp; }
 int tc_decoder_forward(TcDecoder* h, const float* z_dev, int B, float* x_out, cudaStream_t s) {
   TcLayer& D = h->layers[0];
   split_scale_kernel<<<(unsigned)std::min<int64_t>(1024, ceil_div((int64_t)B * D.in_c, 256)), 256, 0, s>>>(z_dev, (long long)B * D.in_c, ACT_SCALE,
-                                                                                                          D.in_hi, D.in_lo);
+                                                                                                          D.in_hi, D.in_lo, h->range_flag, 1u << 15);
   AAE_LAUNCH_OK();
   for (size_t i = 0; i < h->layers.size(); ++i) {
     TcLayer& T = h->layers[i];

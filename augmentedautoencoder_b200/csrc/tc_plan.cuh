@@ -38,7 +38,13 @@ struct TcGemmParams {
   __half* out_hi;
   __half* out_lo;
   float* out_f32;        // OUT_F32: [splits, M, N]
+  // run-time range guard of the static fp16 scaling: an output whose magnitude times out_scale would round to fp16 infinity
+  // (|activation| >= 4094 at scale 16) sets `range_bit` in *range_flag instead of producing inf/garbage silently
+  unsigned* range_flag;
+  unsigned range_bit;
 };
+
+constexpr float TC_F16_OVERFLOW = 65520.f;   // smallest magnitude that rounds to infinity in fp16 (round to nearest even)
 
 
 
@@ -76,9 +82,12 @@ struct TcLayer {
   int kch;    // K chunk per pipeline stage: 64 (128-byte swizzle) or 32 (64-byte swizzle, 4 stages)
 };
 
+// bits of the range flag word: bit l = the activation written by conv layer l (0-based; the decoder counts dense_1 as 0)
+// overflowed; bit 16 + l = a weight of layer l overflowed when it was packed
 struct TcEncoder {
   int device;
   aae_net_cfg cfg;
+  unsigned* range_flag = nullptr;   // device word, see above
   std::vector<TcLayer> layers;   // conv layers 1..L-1 followed by the dense layer
   int flat;
   float* partials = nullptr;     // dense split-K partials [splits, max_batch, latent]
@@ -95,6 +104,7 @@ struct TcEncoder {
 struct TcDecoder {
   int device;
   aae_net_cfg cfg;
+  unsigned* range_flag = nullptr;
   std::vector<TcLayer> layers;     // [0] dense_1, [1..L-1] sub-pixel convs, [L] sub-pixel output layer
   std::vector<float*> bias_dev;    // per layer: bias in GEMM-column order (dense: the caller's; convs: tiled 4x, padded)
   float* wm_tmp = nullptr;         // fp32 merged-weight scratch
@@ -165,8 +175,13 @@ __device__ __forceinline__ void tc_store_chunk(const TcGemmParams& p, const TcRo
     off = ((long long)(r.b * 2 * p.OH + 2 * r.i + (cls >> 1)) * (2 * p.OW) + 2 * r.j + (cls & 1)) * cq + co;
   }
   uint32_t hi[16], lo[16];
+  float amax = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) tc::split_f16x2(f[j] * p.out_scale, f[j + 1] * p.out_scale, hi[j >> 1], lo[j >> 1]);
+  for (int j = 0; j < 32; j += 2) {
+    amax = fmaxf(amax, fmaxf(fabsf(f[j]), fabsf(f[j + 1])));
+    tc::split_f16x2(f[j] * p.out_scale, f[j + 1] * p.out_scale, hi[j >> 1], lo[j >> 1]);
+  }
+  if (p.range_flag != nullptr && !(amax * p.out_scale < TC_F16_OVERFLOW)) atomicOr(p.range_flag, p.range_bit);
   uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
   uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
 #pragma unroll

@@ -130,6 +130,7 @@ class AePoseEstimator(PoseEstInterface):
         for clas, items, idx in pending:     # ... then collect
             cb, sess = self.all_codebooks[clas], self._sessions[clas]
             idcs = idx.cpu().numpy().astype(np.int64)[:, 0]
+            cb._encoder.check_range(sess.device)
             train_args = self.all_train_args[clas]
             K_train = np.array(eval(train_args.get('Dataset', 'K'))).reshape(3, 3)
             radius = train_args.getfloat('Dataset', 'RADIUS')

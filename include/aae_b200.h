@@ -93,6 +93,19 @@ AAE_API int aae_encoder_get_weights(aae_encoder* h, int layer, float* kernel_any
 AAE_API int aae_encoder_forward_u8(aae_encoder* h, const uint8_t* crops_dev, int batch, float* z_out_dev, void* stream);
 /* crops NHWC float32 in [0,1] (the placeholder of auto_pose/ae/ae_factory.py:133). */
 AAE_API int aae_encoder_forward_f32(aae_encoder* h, const float* crops_dev, int batch, float* z_out_dev, void* stream);
+/* Run-time range guard of AAE_PREC_TC_SPLIT.  The tensor-core path stores activations as 16*x and weights as 256*w in fp16
+ * (hi, lo) pairs, i.e. it needs |activation| < 4094 and |weight| < 255.9 -- true for every trained AAE we know of, but not a
+ * law.  A value outside that range is never turned into inf/garbage silently: the kernels record it, aae_*_set_weights
+ * fails with AAE_ERR_UNSUPPORTED when a weight is out of range, and this call (which synchronises `stream`) reports -- and
+ * clears -- an activation overflow of any forward / training step launched on the handle so far, naming the layers in
+ * aae_last_error_string().  The forward entry points stay asynchronous; callers that read results on the host
+ * (Session.run, Codebook.nearest_rotation) call this after their own synchronisation.  AAE_PREC_FP32_SIMT handles have no
+ * such limit and always return AAE_OK.  (The reference's fp32 TF graph has no counterpart: auto_pose/ae/encoder.py:37-68.) */
+AAE_API int aae_encoder_range_status(aae_encoder* h, void* stream);
+/* Device address of the guard's 32-bit word (NULL for AAE_PREC_FP32_SIMT handles): streaming callers copy it to pinned host
+ * memory behind their own results on their own stream and call aae_encoder_range_status only when it is non-zero, so the
+ * pipeline is never synchronised for the check (Codebook.nearest_rotation_async). */
+AAE_API int aae_encoder_range_word(aae_encoder* h, const uint32_t** word_dev);
 /* Device pointer + element count of the activation of conv layer `layer` (NHWC fp32) from the last
  * forward; layer == num_layers gives the flattened encoder_out.  For tests and for the trainer. */
 AAE_API int aae_encoder_activation(aae_encoder* h, int layer, const float** ptr_dev, int64_t* count);
@@ -146,6 +159,9 @@ AAE_API int aae_decoder_destroy(aae_decoder* h);
 AAE_API int aae_decoder_set_weights(aae_decoder* h, int layer, const float* kernel_any, const float* bias_any, void* stream);
 AAE_API int aae_decoder_get_weights(aae_decoder* h, int layer, float* kernel_any, float* bias_any, void* stream);
 AAE_API int aae_decoder_forward(aae_decoder* h, const float* z_dev, int batch, float* x_out_dev, void* stream);
+/* Same contract as aae_encoder_range_status for the decoder (dense_1 counts as layer 0; the latent fed to the decoder is
+ * covered too). */
+AAE_API int aae_decoder_range_status(aae_decoder* h, void* stream);
 /* Bootstrapped L2 (LOSS: L2, BOOTSTRAP_RATIO r): per-sample top-k of the flattened squared error,
  * k = numel/r, mean over the [B,k] survivors (auto_pose/ae/decoder.py:90-101).
  * grad_out_dev (optional, [B,numel]) receives dLoss/dx. */

@@ -259,3 +259,58 @@ def test_inference_after_a_training_step_uses_the_updated_weights(sess):
     enc3, dec3, top3, _, _ = _train_pair(1, 4)
     ref = [float(top3.step_device(xb, yb, update=True)) for _ in range(3)]
     assert abs(l3 - ref[2]) < 1e-6, (l3, ref)
+
+
+def test_range_guard_reports_overflow_instead_of_garbage(sess):
+    """The split-fp16 arithmetic needs |activation| < 4094 and |weight| < 255.9.  A model outside that range
+    must fail loudly -- AAE_ERR_UNSUPPORTED naming the layer -- never return inf / garbage with status 0; the fp32 path takes
+    the same model without complaint."""
+    from augmentedautoencoder_b200._lib import AaeError
+    from augmentedautoencoder_b200.ae.decoder import Decoder
+    from augmentedautoencoder_b200.ae.session import placeholder
+    p = O.make_encoder_params(42, bias_scale=0.05)
+    crops = O.make_crops_u8(5, 3)
+    # (1) a weight the fp16 operands cannot hold is refused when the weights reach the device
+    bad_w = dict(p)
+    bad_w["conv2d_2/kernel"] = p["conv2d_2/kernel"].copy()
+    bad_w["conv2d_2/kernel"][1, 2, 3, 4] = 300.0
+    enc = _enc(1, 4, bad_w)
+    with pytest.raises(AaeError, match=r"weight.*layer\(s\) 2"):
+        sess.run(enc.z, {enc.x: crops})
+    # (2) activations: a large bias pushes conv1's (bit 0, tcgen05 conv1 kernel) / conv2's (bit 1, GEMM epilogue) output past 4094
+    for name, layer in (("conv2d/bias", 0), ("conv2d_1/bias", 1)):
+        bad_a = dict(p)
+        bad_a[name] = p[name].copy()
+        bad_a[name][7] = 5000.0
+        enc = _enc(1, 4, bad_a)
+        for feed in (crops, O.preprocess(crops)):                      # uint8 and float feeds
+            with pytest.raises(AaeError, match=r"activation.*layer\(s\) %d" % layer):
+                sess.run(enc.z, {enc.x: feed})
+        E = O.make_codebook(3, n=36 * 20)
+        cb = _codebook(enc, E, max_batch=4, precision=1)
+        with pytest.raises(AaeError, match="activation"):
+            cb.nearest_rotation(sess, crops, return_idcs=True)
+        with pytest.raises(AaeError, match="activation"):              # streaming call: reported by .result(), no pipeline sync otherwise
+            cb.nearest_rotation_async(sess, torch.from_numpy(crops)).result()
+        enc.load_weights(p)                                            # the guard was cleared by the report: good weights run clean
+        z = sess.run(enc.z, {enc.x: crops})
+        assert np.all(np.isfinite(z))
+        # the exact fp32 path has no such limit
+        enc0 = _enc(0, 4, bad_a)
+        assert np.all(np.isfinite(sess.run(enc0.z, {enc0.x: crops})))
+    # (3) decoder
+    dp = O.make_decoder_params(43, bias_scale=0.05)
+    bad_d = dict(dp)
+    bad_d["dense_1/bias"] = dp["dense_1/bias"].copy()
+    bad_d["dense_1/bias"][11] = 5000.0
+    zin = placeholder(np.float32, [None, 128])
+    dec = Decoder(placeholder(np.float32, [None, 128, 128, 3]), zin, list(reversed(O.NUM_FILTER)), 5, list(reversed(O.STRIDES)), "L2", 4,
+                  False, False, max_batch=4, precision=1)
+    dec.load_weights(bad_d)
+    zz = np.random.RandomState(0).standard_normal((2, 128)).astype(np.float32)
+    with pytest.raises(AaeError, match=r"activation.*layer\(s\) 0"):
+        sess.run(dec.x, {zin: zz})
+    with pytest.raises(AaeError, match="latent"):
+        sess.run(dec.x, {zin: zz * 1e4})
+    dec.load_weights(dp)
+    assert np.all(np.isfinite(sess.run(dec.x, {zin: zz})))
