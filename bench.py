@@ -103,6 +103,25 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def pin_to_gpu_numa(index):
+    """Bind this rank (and the pinned buffers it allocates afterwards) to the CPU cores NVML reports as local to GPU `index`
+    (on the pool's boxes GPUs 0-3 hang off socket 0, GPUs 4-7 off socket 1).  Returns the number of cores, or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def pct(xs, q):
     s = sorted(xs)
     return s[min(len(s) - 1, int(q * len(s)))]
@@ -173,7 +192,7 @@ def run_reference(args, rank, world):
            "config": {"workload": "configs[1]: single object, batch=256 synthetic 128x128x3 uint8 crops, encoder + codebook NN (92232 rows)",
                       "batch_per_call": sample,
                       "note": "restated reference CPU path (oracle port; TensorFlow not installable offline)"},
-           "cpu_baseline": {"value": v, "unit": "queries/s", "cores": os.cpu_count(), "threads": arm.threads[sample], "kind": "port", "sample": desc},
+           "cpu_baseline": {"value": v, "unit": "queries/s", "cores": len(os.sched_getaffinity(0)), "threads": arm.threads[sample], "kind": "port", "sample": desc},
            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -448,6 +467,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from augmentedautoencoder_b200 import _lib, build_ext
+    numa_cores = pin_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -615,7 +635,7 @@ def run_ours(args, rank, world, local_rank):
         arm = CpuArm()
         q64, n64, t64 = arm.qps(10.0, 64)
         q1, n1, t1 = arm.qps(5.0, 1)
-        cpu = {"value": q64, "unit": "queries/s", "cores": os.cpu_count(), "threads": arm.threads[64], "kind": "port",
+        cpu = {"value": q64, "unit": "queries/s", "cores": len(os.sched_getaffinity(0)), "threads": arm.threads[64], "kind": "port",
                "sample": "%d crops in %.1f s, 64 crops per call (bounded sample of the 256-crop batches), torch CPU fp32 oracle with resident variables, "
                          "%d intra-op threads chosen by sweep %s; one crop per call (the reference's per-detection pattern): %.1f queries/s at %d threads"
                          % (n64, t64, arm.threads[64], arm.table[64], q1, arm.threads[1])}
@@ -625,7 +645,7 @@ def run_ours(args, rank, world, local_rank):
            "data": "synthetic",
            "config": {"workload": "configs[1]: single object, batch=256 synthetic 128x128x3 uint8 crops, encoder + fused codebook NN (92232 rows)",
                       "batch_per_gpu": BATCH, "global_batch": BATCH * world, "batches_per_step": M, "timed_batches": n_batches,
-                      "parallelism": "dp%d (independent replicas)" % world,
+                      "parallelism": "dp%d (independent replicas)" % world, "cpu_affinity": "%s cores local to the GPU (NVML)" % numa_cores,
                       "l2": "256 MiB memset between timed batches (untimed) so weights/codebook/crops come from HBM",
                       "precision": args.precision},
            "ms_per_batch": {"mean": ms_per_batch, "median": statistics.median(batch_ms), "p10": pct(batch_ms, 0.1), "p90": pct(batch_ms, 0.9),

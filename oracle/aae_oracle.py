@@ -579,7 +579,7 @@ def best_thread_count(fn, candidates=(1, 2, 4, 8, 16, 32, 64, 128, 256), repeats
     torch set to the fastest.  Returns (threads, seconds per call at that setting, {t: seconds})."""
     import os
     import time
-    ncpu = os.cpu_count() or 1
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)   # the cores this process may use
     cands = sorted({t for t in candidates if min_threads <= t <= ncpu} | {ncpu})
     table = {}
     for t in cands:

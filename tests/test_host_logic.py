@@ -249,3 +249,48 @@ def test_restore_checkpoint_reads_tensorflow_layout(tmp_path):
     assert factory.restore_checkpoint(None, factory.Saver([enc2, cb2]), str(ckdir), at_step=20000).endswith("chkpt-20000")
     with pytest.raises(FileNotFoundError):
         factory.restore_checkpoint(None, factory.Saver([enc2, cb2]), str(ckdir), at_step=12345)
+
+
+def test_reader_on_an_independently_assembled_bundle(golden_dir):
+    """SURVEY 8f N1.  tests/golden/tf_bundle/ was NOT written by this repo's writer: its index values were serialised by
+    google.protobuf from TensorFlow's own message classes (TensorBoard ships them), its checksums come from TensorFlow-team
+    code, and the table container was assembled from the LevelDB format description -- two data shards, several index blocks
+    with shortened separators, restart points, gaps between tensors, a string entry and an unknown field
+    (tests/golden/make_tf_bundle.py).  The reader must return every numeric tensor bit for bit, and restore_checkpoint must
+    fill an encoder + codebook built under the same scope (auto_pose/ae/ae_factory.py:149-172)."""
+    from augmentedautoencoder_b200 import _lib
+    from augmentedautoencoder_b200.ae import factory
+    from augmentedautoencoder_b200.ae import session as S
+    from augmentedautoencoder_b200.ae.codebook import Codebook
+    from augmentedautoencoder_b200.ae.encoder import Encoder
+    from augmentedautoencoder_b200.ae.tf_checkpoint import latest_checkpoint, read_tf_checkpoint
+    d = os.path.join(golden_dir, "tf_bundle")
+    exp = np.load(os.path.join(d, "expected.npz"))
+    got = read_tf_checkpoint(os.path.join(d, "chkpt-30000"), verify_crc=True)
+    assert set(got) == {k.replace("|", "/") for k in exp.files}              # the DT_STRING entry is skipped, nothing else is
+    for k in exp.files:
+        v = got[k.replace("|", "/")]
+        assert v.dtype == exp[k].dtype and v.shape == exp[k].shape and np.array_equal(v, exp[k]), k
+    assert got["obj_07/global_step"].shape == () and int(got["obj_07/global_step"]) == 30000
+    assert latest_checkpoint(d)[0] == os.path.join(d, "chkpt-30000")
+    _lib.lib()
+    ds = Dataset(None, min_n_views=12, num_cyclo=4, radius=700)
+    assert ds.embedding_size == 48
+    with S.variable_scope("obj_07"):
+        enc = Encoder(S.placeholder(np.float32, [None, 32, 32, 3]), 16, [8, 16], 5, [2, 2], False, seed=5)
+        cb = Codebook(enc, ds, True)
+    assert factory.restore_checkpoint(None, factory.Saver([enc, cb]), d) == os.path.join(d, "chkpt-30000")
+    w = enc.get_weights()
+    for name in ("conv2d/kernel", "conv2d/bias", "conv2d_1/kernel", "conv2d_1/bias", "dense/kernel", "dense/bias"):
+        assert np.array_equal(w["obj_07/" + name], exp[("obj_07/" + name).replace("/", "|")])
+    assert np.array_equal(cb.embedding_normalized.value(), exp["obj_07|embedding_normalized"])
+    assert np.array_equal(cb.embed_obj_bbs_var.value(), exp["obj_07|embed_obj_bbs_var"])
+
+
+def test_crc32c_and_mask_agree_with_tensorflows_own_code():
+    tb = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    from augmentedautoencoder_b200.ae.tf_checkpoint import _mask_crc, crc32c
+    rng = np.random.RandomState(1)
+    for n in (0, 1, 7, 64, 1000):
+        b = rng.randint(0, 256, n).astype(np.uint8).tobytes()
+        assert crc32c(b) == tb.crc32c(b) and _mask_crc(crc32c(b)) == tb.masked_crc32c(b)
