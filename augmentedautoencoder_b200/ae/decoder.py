@@ -80,7 +80,7 @@ class Decoder(_DeviceModule):
         def fn(ctx):
             if self not in ctx.touched:
                 ctx.touched.append(self)
-            return self.decode_device(ctx.get(self._latent_code))
+            return self.decode_device(to_device_input(ctx.get(self._latent_code), ctx.session.device))   # a fed latent may be numpy
         return Tensor("conv2d_out/Sigmoid", (None,) + self._out_shape, np.float32, fn)
 
     @staticmethod

@@ -306,6 +306,254 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
   }
 }
 
+
+// =====================================================================================================================
+// uint8 feed, second generation (default for uint8 crops; AAE_C1_V1=1 selects the kernel above for same-box A/B runs).
+// The first kernel ran at 0.35 of the HBM write roofline: 3.9 k shared-memory wavefronts per 128-pixel tile against an HBM
+// budget of 2.8 k cycles per tile.  What changed:
+//   * 1/255 is folded into the packed weights, so the A operand is the BYTE ITSELF as fp16 -- exact, no lo plane: two
+//     products per K step (A*W_hi + A*W_lo) instead of three, half the A-tile bytes, and no lookup table;
+//   * K is laid out as 5 kernel rows x 16 slots (slot 0 of every row meets a zero weight, slots 1..15 are the 15 (kw, c)
+//     taps), so a kernel row of a pixel's patch is 32 contiguous, 4-byte-aligned bytes of the staged input row: 40 LDS.32 +
+//     10 STS.128 per builder thread and tile (before: 80 + 20), bank-conflict free (lane -> pixel order below, 800-byte rows);
+//   * the staged input rows are fp16 written straight from the 16-byte global loads (byte -> fp16 is two PRMT + two HSUB2
+//     per four bytes), double buffered; the A tile is double buffered too, so builders run a tile ahead of the MMAs;
+//   * TMEM lane r is output "slot" r of the tile's 32 KB slab of conv2's space-to-depth input (slot = (ow/2)*4 + (oh%2)*2 +
+//     ow%2), so the staged output tile is the slab in order; it is written in the 128-byte-swizzle layout (conflict-free
+//     STS.128) and leaves through FOUR 16 KB TMA tensor stores per tile (hi/lo x channel halves) instead of 32 bulk copies.
+constexpr int U8_A_STAGES = 2;
+constexpr int U8_A_STAGE = 2 * C1_ATOM;           // K slots [0,64) and [64,80): two 128-row x 128-byte atoms
+constexpr int U8_PIX_LD = 400;                    // fp16 elements per staged input row: 8 lead-in + 384 data + 8 tail
+constexpr int U8_PIX_BUF = C1_PIX_ROWS * U8_PIX_LD * 2;   // bytes
+constexpr int U8_W_BYTES = 4 * C1_ATOM;
+constexpr int U8_OUT_BYTES = 4 * C1_ATOM;         // hi ch[0,64), hi ch[64,128), lo ch[0,64), lo ch[64,128): 128 slots x 128 B each
+constexpr int U8_SMEM_TOTAL = U8_W_BYTES + U8_A_STAGES * U8_A_STAGE + U8_OUT_BYTES + 2 * U8_PIX_BUF + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// four bytes -> four fp16 (exact): 0x6400 | b is the fp16 1024 + b, minus 1024
+__device__ __forceinline__ void bytes_to_half4(uint32_t x, uint32_t& lo2, uint32_t& hi2) {
+  const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
+  const uint32_t a = __byte_perm(x, 0x64646464u, 0x4140), b = __byte_perm(x, 0x64646464u, 0x4342);
+  const __half2 ha = __hsub2(*reinterpret_cast<const __half2*>(&a), k1024), hb = __hsub2(*reinterpret_cast<const __half2*>(&b), k1024);
+  lo2 = *reinterpret_cast<const uint32_t*>(&ha);
+  hi2 = *reinterpret_cast<const uint32_t*>(&hb);
+}
+
+__global__ void __launch_bounds__(C1_THREADS, 1)
+tc_conv1_u8_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                   const __grid_constant__ CUtensorMap tm_out_hi, const __grid_constant__ CUtensorMap tm_out_lo, const Conv1Params p) {
+  constexpr int N = 128, CIN = 3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_smem = smem;                                   // hi k0, hi k1, lo k0, lo k1 (128 rows x 128 B each)
+  uint8_t* a_smem = w_smem + U8_W_BYTES;
+  uint8_t* out_smem = a_smem + U8_A_STAGES * U8_A_STAGE;
+  uint8_t* pix = out_smem + U8_OUT_BYTES;                   // [2][C1_PIX_ROWS][U8_PIX_LD] fp16
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(pix + 2 * U8_PIX_BUF);
+  uint64_t* a_full = w_full + 1;
+  uint64_t* a_empty = a_full + U8_A_STAGES;
+  uint64_t* acc_full = a_empty + U8_A_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  __shared__ float bias_s[N];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int TMEM_COLS = 2 * N;
+  if (threadIdx.x < N) bias_s[threadIdx.x] = p.bias[threadIdx.x] * p.out_scale;     // relu(x) * s == relu(x * s) for s > 0
+  for (int i = threadIdx.x; i < 2 * U8_PIX_BUF / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(pix)[i] = 0u;   // lead-in / tail stay zero
+  if (warp == C1_MMA_WARP && lane == 0) {
+    prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo); prefetch_tmap(&tm_out_hi); prefetch_tmap(&tm_out_lo);
+    mbar_init(w_full, 1);
+    for (int s = 0; s < U8_A_STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], C1_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == C1_MMA_WARP) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int hw = p.OH * p.OW;
+
+  if (warp < 4) {
+    // ===================== A builders: thread r owns output slot r of the tile =====================
+    const int r = threadIdx.x;
+    const int ow = ((r >> 2) << 1) | (r & 1), dr = (r >> 1) & 1;
+    constexpr int ROW16 = 128 * CIN / 16;                    // 16-byte pieces per input row (24)
+    constexpr int NPIECE = C1_PIX_ROWS * ROW16;              // 168 per tile: threads 0..127 take one, threads 0..39 a second
+    uint4 raw[2];
+    auto fetch = [&](int tile) {                             // global -> registers (rows outside the image: zeros)
+      const int m_first = tile * 128;
+      const int b = m_first / hw, oh0 = (m_first - b * hw) / p.OW;
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int u = r + v * 128;
+        raw[v] = make_uint4(0u, 0u, 0u, 0u);
+        const int row = u / ROW16, c16 = u - row * ROW16;
+        const int ih = 2 * oh0 - p.pad_t + row;
+        if (u < NPIECE && b < p.B && ih >= 0 && ih < p.H)
+          raw[v] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + ((long long)(b * p.H + ih) * p.W) * CIN) + c16);
+      }
+    };
+    auto stage = [&](uint8_t* buf) {                         // registers -> fp16 staged rows (data starts 8 elements into a row)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int u = r + v * 128;
+        if (u < NPIECE) {
+          const int row = u / ROW16, c16 = u - row * ROW16;
+          uint4 o0, o1;
+          bytes_to_half4(raw[v].x, o0.x, o0.y);
+          bytes_to_half4(raw[v].y, o0.z, o0.w);
+          bytes_to_half4(raw[v].z, o1.x, o1.y);
+          bytes_to_half4(raw[v].w, o1.z, o1.w);
+          uint4* dst = reinterpret_cast<uint4*>(buf + row * (U8_PIX_LD * 2) + 16 + c16 * 32);
+          dst[0] = o0;
+          dst[1] = o1;
+        }
+      }
+    };
+    if (my_tiles > 0) {
+      fetch((int)blockIdx.x);
+      stage(pix);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int i = 0; i < my_tiles; ++i) {
+      const int s = i % U8_A_STAGES;
+      const bool more = i + 1 < my_tiles;
+      if (more) fetch((int)blockIdx.x + (i + 1) * (int)gridDim.x);
+      // kernel row kh of this pixel's patch = elements [4 + 6*ow, +16) of staged row 2*dr + kh: slot 0 is the element before the
+      // patch (zero weight), slots 1..15 the 5 x 3 taps
+      const uint8_t* src = pix + (i & 1) * U8_PIX_BUF + (2 * dr) * (U8_PIX_LD * 2) + (4 + 6 * ow) * 2;
+      mbar_wait(&a_empty[s], ((uint32_t)(i / U8_A_STAGES) & 1u) ^ 1u);
+      uint8_t* st = a_smem + s * U8_A_STAGE;
+#pragma unroll
+      for (int kh = 0; kh < 5; ++kh) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(src + kh * (U8_PIX_LD * 2));
+        const uint4 c0 = make_uint4(q[0], q[1], q[2], q[3]), c1 = make_uint4(q[4], q[5], q[6], q[7]);
+        const int atom = kh >> 2, ci = (kh & 3) * 2;
+        uint8_t* row = st + atom * C1_ATOM + r * 128;
+        *reinterpret_cast<uint4*>(row + (((ci) ^ (r & 7)) << 4)) = c0;
+        *reinterpret_cast<uint4*>(row + (((ci + 1) ^ (r & 7)) << 4)) = c1;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[s]);
+      if (more) stage(pix + ((i + 1) & 1) * U8_PIX_BUF);    // that buffer's last readers (tile i-1) passed the barrier below an iteration ago
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  } else if (warp < C1_MMA_WARP) {
+    // ===================== epilogue: TMEM -> bias + ReLU + (hi, lo) split -> swizzled staging -> TMA tensor stores =====================
+    const int q = warp & 3, hsel = (warp - 4) >> 2, r = q * 32 + lane;
+    const float us = p.unscale * p.out_scale;
+    uint8_t* my_hi = out_smem + hsel * C1_ATOM + r * 128;
+    uint8_t* my_lo = my_hi + 2 * C1_ATOM;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int as = i & 1;
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      mbar_wait(&acc_full[as], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      if (i > 0) {                                   // the previous tile's tensor stores must have finished reading the staging
+        if (warp == 4) bulk_wait_read_all();         // (meaningful in lane 0, which committed the stores)
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_EPI_WARPS) : "memory");
+      }
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + hsel * 64 + cc * 32), v);
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float a = fmaxf(fmaf(__uint_as_float(v[j]), us, bias_s[hsel * 64 + cc * 32 + j]), 0.f);
+          const float bb = fmaxf(fmaf(__uint_as_float(v[j + 1]), us, bias_s[hsel * 64 + cc * 32 + j + 1]), 0.f);
+          amax = fmaxf(amax, fmaxf(a, bb));
+          split_f16x2(a, bb, hi[j >> 1], lo[j >> 1]);
+        }
+        if (p.range_flag != nullptr && !(amax < 65520.f)) atomicOr(p.range_flag, 1u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = ((cc * 4 + j) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(my_hi + ch) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<uint4*>(my_lo + ch) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA engine
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_EPI_WARPS) : "memory");
+      if (warp == 4 && lane == 0) {
+        const int slot0 = tile * 128;                // slots are in tile order: tile t covers slots [128 t, 128 t + 128)
+        tma_store_3d(&tm_out_hi, out_smem, 0, 0, slot0);
+        tma_store_3d(&tm_out_hi, out_smem + C1_ATOM, 0, 1, slot0);
+        tma_store_3d(&tm_out_lo, out_smem + 2 * C1_ATOM, 0, 0, slot0);
+        tma_store_3d(&tm_out_lo, out_smem + 3 * C1_ATOM, 0, 1, slot0);
+        bulk_commit_group();
+      }
+    }
+    if (warp == 4 && lane == 0) bulk_wait_all();     // all stores landed before the CTA exits
+  } else {
+    // ===================== weight TMA + MMA issuer (last warp) =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, U8_W_BYTES);
+      tma_load_2d(w_smem, &tm_w_hi, w_full, 0, 0);
+      tma_load_2d(w_smem + C1_ATOM, &tm_w_hi, w_full, 64, 0);
+      tma_load_2d(w_smem + 2 * C1_ATOM, &tm_w_lo, w_full, 0, 0);
+      tma_load_2d(w_smem + 3 * C1_ATOM, &tm_w_lo, w_full, 64, 0);
+      mbar_wait(w_full, 0);
+      constexpr uint32_t idesc = make_idesc_f16(128, N, 0);
+      const uint32_t wst = smem_u32(w_smem);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % U8_A_STAGES, as = i & 1;
+        mbar_wait(&acc_empty[as], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        mbar_wait(&a_full[s], (uint32_t)(i / U8_A_STAGES) & 1u);
+        tc_fence_after();
+        const uint32_t ast = smem_u32(a_smem + s * U8_A_STAGE);
+        const uint32_t d = tmem_base + (uint32_t)(as * N);
+#pragma unroll
+        for (int k = 0; k < C1_KPAD / 16; ++k) {
+          const int atom = k >> 2, kk = k & 3;
+          const uint64_t a = desc_advance_k(make_sw128_kmajor_desc(ast + atom * C1_ATOM), kk);
+          const uint64_t w_hi = desc_advance_k(make_sw128_kmajor_desc(wst + atom * C1_ATOM), kk);
+          const uint64_t w_lo = desc_advance_k(make_sw128_kmajor_desc(wst + (2 + atom) * C1_ATOM), kk);
+          umma_f16(d, a, w_lo, idesc, k > 0 ? 1u : 0u);
+          umma_f16(d, a, w_hi, idesc, 1u);
+        }
+        umma_commit(&a_empty[s]);
+        umma_commit(&acc_full[as]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C1_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// W fp32 [75][N] (HWIO flattened) -> (hi, lo) fp16 [N][128] in the 5 x 16 slot order of the uint8 kernel: slot kh*16 + 1 + (kw*3 + c)
+// holds scale * W[kh][kw][c][n] (scale = 2^16 / 255: the x/255 of codebook.py:58-59 lives here), every other slot is zero
+__global__ void pack_conv1_u8_weights_kernel(const float* __restrict__ w, int N, float scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                                             unsigned* __restrict__ range_flag, unsigned range_bit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 128) return;
+  const int n = i / 128, k = i - n * 128;
+  const int kh = k >> 4, j = k & 15;
+  const float v = (kh < 5 && j >= 1) ? w[(long long)(kh * 15 + j - 1) * N + n] * scale : 0.f;
+  if (range_flag != nullptr && !(fabsf(v) < 65520.f)) atomicOr(range_flag, range_bit);
+  __half h, l;
+  split_f16(v, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+
 // W fp32 [75][N] (HWIO flattened) -> (hi, lo) fp16 [N][128] K-major, scaled, zero for k >= K
 __global__ void pack_conv1_weights_kernel(const float* __restrict__ w, int K, int N, float scale, __half* __restrict__ hi, __half* __restrict__ lo,
                                           unsigned* __restrict__ range_flag, unsigned range_bit) {
@@ -326,6 +574,12 @@ struct TcConv1 {
   int N, sm_count;
   __half *w_hi = nullptr, *w_lo = nullptr;
   CUtensorMap tm_hi, tm_lo;
+  // uint8 kernel: weights with 1/255 folded in, 5 x 16 slot order; output tensor maps over conv2's (hi, lo) input
+  __half *w8_hi = nullptr, *w8_lo = nullptr;
+  CUtensorMap tm8_hi, tm8_lo, tm_out_hi, tm_out_lo;
+  const __half *bound_hi = nullptr, *bound_lo = nullptr;
+  long long slots = 0;            // 256-byte output slots the tensor maps cover ((b, oh/2, ow/2, parity) positions)
+  bool u8_ok = false;
 };
 
 bool tc_conv1_supported(const aae_net_cfg* cfg) {
@@ -349,6 +603,15 @@ int tc_conv1_create(int device, const aae_net_cfg* cfg, TcConv1** out) {
   const uint32_t box[2] = {64, (uint32_t)h->N};
   int st = make_tmap_f16(&h->tm_hi, h->w_hi, 2, dims, strides, box);
   if (st == AAE_OK) st = make_tmap_f16(&h->tm_lo, h->w_lo, 2, dims, strides, box);
+  if (st == AAE_OK && h->N == 128 && getenv("AAE_C1_V1") == nullptr) {
+    e = cudaMalloc(&h->w8_hi, (size_t)h->N * 128 * sizeof(__half));
+    if (e == cudaSuccess) e = cudaMalloc(&h->w8_lo, (size_t)h->N * 128 * sizeof(__half));
+    if (e != cudaSuccess) { set_error("tc conv1 alloc failed: %s", cudaGetErrorString(e)); tc_conv1_destroy(h); return AAE_ERR_OOM; }
+    st = make_tmap_f16(&h->tm8_hi, h->w8_hi, 2, dims, strides, box);
+    if (st == AAE_OK) st = make_tmap_f16(&h->tm8_lo, h->w8_lo, 2, dims, strides, box);
+    if (st == AAE_OK) st = cudaFuncSetAttribute(tc_conv1_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U8_SMEM_TOTAL) == cudaSuccess ? AAE_OK : AAE_ERR_CUDA;
+    h->u8_ok = st == AAE_OK;
+  }
   if (st != AAE_OK) { tc_conv1_destroy(h); return st; }
   *out = h;
   return AAE_OK;
@@ -356,13 +619,19 @@ int tc_conv1_create(int device, const aae_net_cfg* cfg, TcConv1** out) {
 
 void tc_conv1_destroy(TcConv1* h) {
   if (!h) return;
-  cudaFree(h->w_hi); cudaFree(h->w_lo);
+  cudaFree(h->w_hi); cudaFree(h->w_lo); cudaFree(h->w8_hi); cudaFree(h->w8_lo);
   delete h;
 }
 
 int tc_conv1_pack(TcConv1* h, const float* w_dev, int K, float w_scale, unsigned* range_flag, unsigned range_bit, cudaStream_t s) {
   pack_conv1_weights_kernel<<<(unsigned)ceil_div(h->N * 128, 256), 256, 0, s>>>(w_dev, K, h->N, w_scale, h->w_hi, h->w_lo, range_flag, range_bit);
   AAE_LAUNCH_OK();
+  if (h->u8_ok) {
+    AAE_REQUIRE(K == 75, "tc conv1 (uint8 kernel): K = %d, expected 75", K);
+    pack_conv1_u8_weights_kernel<<<(unsigned)ceil_div(h->N * 128, 256), 256, 0, s>>>(w_dev, h->N, w_scale * 256.f / 255.f, h->w8_hi, h->w8_lo, range_flag,
+                                                                                    range_bit);
+    AAE_LAUNCH_OK();
+  }
   return AAE_OK;
 }
 
@@ -384,7 +653,21 @@ int tc_conv1_forward(TcConv1* h, const aae_net_cfg* cfg, const void* crops, int 
   p.out_hi = out_hi; p.out_lo = out_lo;
   const int grid = std::min(h->sm_count, p.num_tiles);
   using S = Conv1Smem<128>;
-  if (src_u8) {
+  if (src_u8 && h->u8_ok && (reinterpret_cast<uintptr_t>(crops) & 15u) == 0) {   // 16-byte row pieces are loaded as uint4
+    // output tensor maps: [slot][half][64 channels] views of conv2's (hi, lo) input; the buffers hold max_batch crops, this call
+    // may be shorter -- the maps cover exactly the slots this call writes
+    const long long slots = (long long)p.num_tiles * 128;
+    if (h->bound_hi != out_hi || h->bound_lo != out_lo || h->slots != slots) {
+      const uint64_t dims[3] = {64, 2, (uint64_t)slots};
+      const uint64_t strides[2] = {128, 256};
+      const uint32_t box[3] = {64, 1, 128};
+      AAE_TRY(make_tmap_f16(&h->tm_out_hi, out_hi, 3, dims, strides, box));
+      AAE_TRY(make_tmap_f16(&h->tm_out_lo, out_lo, 3, dims, strides, box));
+      h->bound_hi = out_hi; h->bound_lo = out_lo; h->slots = slots;
+    }
+    p.unscale = 1.f / (w_scale * 256.f);              // accumulators hold sum u8 * (w * w_scale * 256 / 255)
+    tc_conv1_u8_kernel<<<grid, C1_THREADS, U8_SMEM_TOTAL, s>>>(h->tm8_hi, h->tm8_lo, h->tm_out_hi, h->tm_out_lo, p);
+  } else if (src_u8) {
     AAE_CUDA_OK(cudaFuncSetAttribute(tc_conv1_kernel<128, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     tc_conv1_kernel<128, 3, true><<<grid, C1_THREADS, S::TOTAL, s>>>(h->tm_hi, h->tm_lo, p);
   } else {

@@ -12,7 +12,7 @@ args = sys.argv[1:]
 env_set = dict(a.split("=", 1) for a in args if "=" in a and not a.startswith("--"))
 rounds = int(args[args.index("--rounds") + 1]) if "--rounds" in args else 3
 workload = args[args.index("--workload") + 1] if "--workload" in args else "infer"
-cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "3", "--no-cpu-baseline", "--workload", workload]
+cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--warmup", "3", "--no-cpu-baseline", "--no-parity", "--workload", workload]
 res = {"base": [], "variant": []}
 for r in range(rounds):
     for name in ("base", "variant"):
