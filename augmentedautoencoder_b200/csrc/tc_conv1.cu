@@ -320,7 +320,8 @@ tc_conv1_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_consta
 //     per four bytes), double buffered; the A tile is double buffered too, so builders run a tile ahead of the MMAs;
 //   * TMEM lane r is output "slot" r of the tile's 32 KB slab of conv2's space-to-depth input (slot = (ow/2)*4 + (oh%2)*2 +
 //     ow%2), so the staged output tile is the slab in order; it is written in the 128-byte-swizzle layout (conflict-free
-//     STS.128) and leaves through FOUR 16 KB TMA tensor stores per tile (hi/lo x channel halves) instead of 32 bulk copies.
+//     STS.128) and leaves through eight 8 KB TMA tensor stores per tile, issued in two phases so that the staging double-buffers
+//     itself (instead of 32 bulk copies behind a full stop).
 constexpr int U8_A_STAGES = 2;
 constexpr int U8_A_STAGE = 2 * C1_ATOM;           // K slots [0,64) and [64,80): two 128-row x 128-byte atoms
 constexpr int U8_PIX_LD = 400;                    // fp16 elements per staged input row: 8 lead-in + 384 data + 8 tail
@@ -329,11 +330,12 @@ constexpr int U8_W_BYTES = 4 * C1_ATOM;
 constexpr int U8_OUT_BYTES = 4 * C1_ATOM;         // hi ch[0,64), hi ch[64,128), lo ch[0,64), lo ch[64,128): 128 slots x 128 B each
 constexpr int U8_SMEM_TOTAL = U8_W_BYTES + U8_A_STAGES * U8_A_STAGE + U8_OUT_BYTES + 2 * U8_PIX_BUF + 1024 /*align*/ + 256 /*barriers*/;
 
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // four bytes -> four fp16 (exact): 0x6400 | b is the fp16 1024 + b, minus 1024
 __device__ __forceinline__ void bytes_to_half4(uint32_t x, uint32_t& lo2, uint32_t& hi2) {
@@ -448,21 +450,22 @@ tc_conv1_u8_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
     }
   } else if (warp < C1_MMA_WARP) {
     // ===================== epilogue: TMEM -> bias + ReLU + (hi, lo) split -> swizzled staging -> TMA tensor stores =====================
+    // The staging is eight 8 KB sub-tiles [hi|lo][channel half][32-channel chunk] of 128 slots x 64 B in the 64-byte-swizzle
+    // layout (conflict-free STS.128 from a thread-per-slot warp).  A tile is shipped in two phases (chunk 0 of both halves, then
+    // chunk 1): the stores of one phase drain while the other phase is being computed, so the 64 KB staging acts as a double
+    // buffer -- the epilogue never waits for its own stores unless HBM is the limit.
     const int q = warp & 3, hsel = (warp - 4) >> 2, r = q * 32 + lane;
     const float us = p.unscale * p.out_scale;
-    uint8_t* my_hi = out_smem + hsel * C1_ATOM + r * 128;
-    uint8_t* my_lo = my_hi + 2 * C1_ATOM;
+    constexpr int SUB = 128 * 64;                    // bytes of one sub-tile
+    const int rsw = (r >> 1) & 3;
+    int phase = 0;                                   // phases issued so far by this CTA (two per tile)
     for (int i = 0; i < my_tiles; ++i) {
       const int as = i & 1;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       mbar_wait(&acc_full[as], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
-      if (i > 0) {                                   // the previous tile's tensor stores must have finished reading the staging
-        if (warp == 4) bulk_wait_read_all();         // (meaningful in lane 0, which committed the stores)
-        asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_EPI_WARPS) : "memory");
-      }
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
+      for (int cc = 0; cc < 2; ++cc, ++phase) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + hsel * 64 + cc * 32), v);
         tmem_ld_wait();
@@ -476,25 +479,34 @@ tc_conv1_u8_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
           split_f16x2(a, bb, hi[j >> 1], lo[j >> 1]);
         }
         if (p.range_flag != nullptr && !(amax < 65520.f)) atomicOr(p.range_flag, 1u);
+        if (phase >= 2) {                            // this phase's sub-tiles were last shipped two phases ago: that group must have been read
+          if (warp == 4) bulk_wait_read_1();         // (meaningful in lane 0, which committed the stores: at most the newest group may be pending)
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_EPI_WARPS) : "memory");
+        }
+        uint8_t* my_hi = out_smem + ((0 * 2 + hsel) * 2 + cc) * SUB + r * 64;
+        uint8_t* my_lo = out_smem + ((1 * 2 + hsel) * 2 + cc) * SUB + r * 64;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int ch = ((cc * 4 + j) ^ (r & 7)) << 4;
+          const int ch = (j ^ rsw) << 4;
           *reinterpret_cast<uint4*>(my_hi + ch) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
           *reinterpret_cast<uint4*>(my_lo + ch) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
-      fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA engine
-      asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_EPI_WARPS) : "memory");
-      if (warp == 4 && lane == 0) {
-        const int slot0 = tile * 128;                // slots are in tile order: tile t covers slots [128 t, 128 t + 128)
-        tma_store_3d(&tm_out_hi, out_smem, 0, 0, slot0);
-        tma_store_3d(&tm_out_hi, out_smem + C1_ATOM, 0, 1, slot0);
-        tma_store_3d(&tm_out_lo, out_smem + 2 * C1_ATOM, 0, 0, slot0);
-        tma_store_3d(&tm_out_lo, out_smem + 3 * C1_ATOM, 0, 1, slot0);
-        bulk_commit_group();
+        if (cc == 1) {                               // both chunks of this warp's TMEM columns have been read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        fence_proxy_async_smem();                    // generic-proxy writes -> visible to the TMA engine
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_EPI_WARPS) : "memory");
+        if (warp == 4 && lane == 0) {
+          const int slot0 = tile * 128;              // slots are in tile order: tile t covers slots [128 t, 128 t + 128)
+#pragma unroll
+          for (int hs = 0; hs < 2; ++hs) {
+            tma_store_2d(&tm_out_hi, out_smem + ((0 * 2 + hs) * 2 + cc) * SUB, hs * 64 + cc * 32, slot0);
+            tma_store_2d(&tm_out_lo, out_smem + ((1 * 2 + hs) * 2 + cc) * SUB, hs * 64 + cc * 32, slot0);
+          }
+          bulk_commit_group();
+        }
       }
     }
     if (warp == 4 && lane == 0) bulk_wait_all();     // all stores landed before the CTA exits
@@ -654,15 +666,15 @@ int tc_conv1_forward(TcConv1* h, const aae_net_cfg* cfg, const void* crops, int 
   const int grid = std::min(h->sm_count, p.num_tiles);
   using S = Conv1Smem<128>;
   if (src_u8 && h->u8_ok && (reinterpret_cast<uintptr_t>(crops) & 15u) == 0) {   // 16-byte row pieces are loaded as uint4
-    // output tensor maps: [slot][half][64 channels] views of conv2's (hi, lo) input; the buffers hold max_batch crops, this call
+    // output tensor maps: [slot][128 channels] views of conv2's (hi, lo) input; the buffers hold max_batch crops, this call
     // may be shorter -- the maps cover exactly the slots this call writes
     const long long slots = (long long)p.num_tiles * 128;
     if (h->bound_hi != out_hi || h->bound_lo != out_lo || h->slots != slots) {
-      const uint64_t dims[3] = {64, 2, (uint64_t)slots};
-      const uint64_t strides[2] = {128, 256};
-      const uint32_t box[3] = {64, 1, 128};
-      AAE_TRY(make_tmap_f16(&h->tm_out_hi, out_hi, 3, dims, strides, box));
-      AAE_TRY(make_tmap_f16(&h->tm_out_lo, out_lo, 3, dims, strides, box));
+      const uint64_t dims[2] = {128, (uint64_t)slots};
+      const uint64_t strides[1] = {256};
+      const uint32_t box[2] = {32, 128};                    // 32 channels x 128 slots = one 8 KB staging sub-tile, 64-byte swizzle
+      AAE_TRY(make_tmap_f16(&h->tm_out_hi, out_hi, 2, dims, strides, box, 64));
+      AAE_TRY(make_tmap_f16(&h->tm_out_lo, out_lo, 2, dims, strides, box, 64));
       h->bound_hi = out_hi; h->bound_lo = out_lo; h->slots = slots;
     }
     p.unscale = 1.f / (w_scale * 256.f);              // accumulators hold sum u8 * (w * w_scale * 256 / 255)

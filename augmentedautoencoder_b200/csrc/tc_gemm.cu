@@ -659,7 +659,25 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     auto qk = tc_gemm4p_kernel<STAGES, KCH>;
     AAE_CUDA_OK(cudaFuncSetAttribute(qk, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    qk<<<dim3(4u * (unsigned)std::min(tiles, std::max(1, sms / 4))), tc_block_threads(), S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w4_hi, L.tm_w4_lo, L.gp, sch);
+    // clusters of four must sit inside one GPC: fewer than sms / 4 of them may be resident at once, and a persistent grid
+    // larger than that would run its tail as a second wave
+    static int quad_slots = 0;
+    if (quad_slots == 0) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(4u * (unsigned)std::max(1, sms / 4));
+      cfg.blockDim = dim3((unsigned)tc_block_threads());
+      cfg.dynamicSmemBytes = S::TOTAL;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = 4; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, qk, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = std::max(1, sms / 4); }
+      quad_slots = n;
+      if (getenv("AAE_TC_VERBOSE")) fprintf(stderr, "[tc] clusters of 4 resident at once: %d (of %d SMs / 4 = %d)\n", n, sms, sms / 4);
+    }
+    qk<<<dim3(4u * (unsigned)std::min(tiles, quad_slots)), tc_block_threads(), S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w4_hi, L.tm_w4_lo, L.gp, sch);
     AAE_LAUNCH_OK();
     return AAE_OK;
   }
@@ -667,15 +685,27 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
     TcTileSched sch;
     sch.m_pairs = (int)((grid.x + 1) / 2); sch.n_tiles = (int)grid.y; sch.splits = (int)grid.z;
     const int tiles = sch.m_pairs * sch.n_tiles * sch.splits;
-    static int pair_slots = 0;                       // CTA pairs that can be resident at once (one per SM pair)
+    auto pk = tc_gemm2p_kernel<STAGES, KCH>;
+    AAE_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    static int pair_slots = 0;                       // CTA pairs that can be resident at once (asked from the driver: pairs cannot straddle GPCs)
     if (pair_slots == 0) {
       int dev = 0, sms = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      pair_slots = std::max(1, sms / 2);
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2u * (unsigned)std::max(1, sms / 2));
+      cfg.blockDim = dim3((unsigned)tc_block_threads());
+      cfg.dynamicSmemBytes = S::TOTAL;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, pk, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = std::max(1, sms / 2); }
+      pair_slots = std::min(n, std::max(1, sms / 2));
+      if (getenv("AAE_TC_VERBOSE")) fprintf(stderr, "[tc] CTA pairs resident at once: %d (of %d SMs / 2 = %d)\n", n, sms, sms / 2);
     }
-    auto pk = tc_gemm2p_kernel<STAGES, KCH>;
-    AAE_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     pk<<<dim3(2u * (unsigned)std::min(tiles, pair_slots)), tc_block_threads(), S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w2_hi, L.tm_w2_lo, L.gp, sch);
     AAE_LAUNCH_OK();
     return AAE_OK;

@@ -60,10 +60,11 @@ __device__ __forceinline__ float tc_dyn_unscale(unsigned amax_bits) { return __i
 constexpr float ACT_SCALE = 16.f;     // activations (and the [0,1] input) are stored as 16 * x
 constexpr float W_SCALE = 256.f;      // weights are stored as 256 * w
 constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 384;       // warp 0 TMA, 1 MMA, 2 TMEM allocator, 3 idle, 4-11 epilogue (two per TMEM lane quadrant)
-// AAE_TC_EPI4=1 launches 256 threads (one epilogue warp per quadrant) for A/B measurements
+constexpr int TC_THREADS = 512;       // launch bound: warp 0 TMA, 1 MMA, 2 TMEM allocator, 3 idle, 4.. epilogue (up to three per TMEM lane quadrant)
+// threads actually launched: 384 (two epilogue warps per quadrant) by default; AAE_TC_EPI4=1 -> 256 (one per quadrant),
+// AAE_TC_EPI12=1 -> 512 (three per quadrant) for A/B measurements
 inline int tc_block_threads() {
-  static const int n = getenv("AAE_TC_EPI4") ? 256 : TC_THREADS;
+  static const int n = getenv("AAE_TC_EPI4") ? 256 : (getenv("AAE_TC_EPI12") ? 512 : 384);
   return n;
 }
 
