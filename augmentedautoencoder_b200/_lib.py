@@ -63,6 +63,9 @@ _SIGS = {
     "aae_trainer_get_grads": (_I, [_P, _I, _I, _P, _P, _P]),
     "aae_trainer_global_step": (_L, [_P]),
     "aae_trainer_profile": (_I, [_P, _I, _P, _I]),
+    "aae_trainer_get_state": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
+    "aae_trainer_set_state": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
+    "aae_trainer_set_global_step": (_I, [_P, _L]),
     "aae_extract_square_patches": (_I, [_P, _I, _I, _P, _I, _F, _I, _P, _P]),
     "aae_augment_batch": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
 }

@@ -156,6 +156,60 @@ class TrainOp(Tensor):
                 ctx.touched.append(m)
         return self.step_device(x, y, update=True)
 
+    # -- optimizer state under TensorFlow's names: "<var>/Adam", "<var>/Adam_1", "<scope>/beta1_power", "<scope>/beta2_power" ------
+    def _scope_prefix(self):
+        name = self._ae._encoder._var_shapes[0][0]                    # e.g. "obj_05/conv2d/kernel"
+        return name.rsplit("/", 2)[0] + "/" if name.count("/") >= 2 else ""
+
+    def optimizer_variables(self, device=None):
+        """{TF name: array} of the Adam slots and beta powers (what tf.train.Saver stores beside the weights, ae_train.py:82).
+        Empty until a trainer exists (no step has run): a fresh optimizer has nothing to save."""
+        if not self._trainers:
+            return {}
+        dev = next(iter(self._trainers)) if device is None else (device.index if isinstance(device, torch.device) else int(device))
+        h = self._trainers[dev]
+        out = {}
+        with torch.cuda.device(dev):
+            for which, mod in ((0, self._ae._encoder), (1, self._ae._decoder)):
+                for i, (kn, ks, bn, bs) in enumerate(mod._var_shapes):
+                    km, kv, bm, bv = np.empty(ks, np.float32), np.empty(ks, np.float32), np.empty(bs, np.float32), np.empty(bs, np.float32)
+                    _lib.check(_lib.lib().aae_trainer_get_state(h, which, i, _lib.ptr(km), _lib.ptr(kv), _lib.ptr(bm), _lib.ptr(bv), None), "get_state")
+                    out[kn + "/Adam"], out[kn + "/Adam_1"], out[bn + "/Adam"], out[bn + "/Adam_1"] = km, kv, bm, bv
+            step = int(_lib.lib().aae_trainer_global_step(h))
+        lr, b1, b2, eps = self._hp
+        # TF keeps beta^(t+1) after t updates (initialised to beta, multiplied once per apply)
+        out[self._scope_prefix() + "beta1_power"] = np.asarray(b1 ** (step + 1), dtype=np.float32)
+        out[self._scope_prefix() + "beta2_power"] = np.asarray(b2 ** (step + 1), dtype=np.float32)
+        return out
+
+    def load_optimizer_variables(self, weights, device, global_step=None):
+        """Restore the Adam slots (and the update count) from a checkpoint dict; returns the names it used.  Variables without
+        slots in the dict keep their current (zero) moments -- a weights-only checkpoint restarts the optimizer, as in TF."""
+        h = self.trainer(device)
+        used = []
+        with torch.cuda.device(device):
+            for which, mod in ((0, self._ae._encoder), (1, self._ae._decoder)):
+                for i, (kn, ks, bn, bs) in enumerate(mod._var_shapes):
+                    arrs = []
+                    for name, shape in ((kn + "/Adam", ks), (kn + "/Adam_1", ks), (bn + "/Adam", bs), (bn + "/Adam_1", bs)):
+                        a = weights.get(name)
+                        if a is not None:
+                            a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+                            if a.shape != tuple(shape):
+                                raise ValueError("%s: shape %s != expected %s" % (name, a.shape, tuple(shape)))
+                            used.append(name)
+                        arrs.append(a)
+                    if any(a is not None for a in arrs):
+                        _lib.check(_lib.lib().aae_trainer_set_state(h, which, i, *[_lib.ptr(a) for a in arrs], None), "set_state")
+            step = global_step
+            b1p = weights.get(self._scope_prefix() + "beta1_power")
+            if step is None and b1p is not None and 0.0 < float(b1p) < 1.0:
+                step = int(round(np.log(float(b1p)) / np.log(self._hp[1]))) - 1
+            if step is not None:
+                _lib.check(_lib.lib().aae_trainer_set_global_step(h, int(max(step, 0))), "set_global_step")
+                self._ae.global_step._host = np.asarray(int(max(step, 0)), dtype=np.int64)
+        return used
+
     def gradients(self, device):
         """{variable name: gradient} from the last forward/backward (for parity tests)."""
         h = self.trainer(device)
@@ -212,9 +266,13 @@ class Saver(object):
     """tf.train.Saver stand-in over a list of modules (Encoder / Decoder / Codebook).  Checkpoints are ``chkpt-<step>.npz``
     files holding the reference's variable names (encoder.py / decoder.py / codebook.py scopes) in the reference's layouts."""
 
-    def __init__(self, modules, global_step=None):
+    def __init__(self, modules, global_step=None, train_op=None):
+        """modules: Encoder / Decoder / Codebook objects.  train_op (a TrainOp): also save / restore the optimizer state under
+        TensorFlow's slot names, so that training resumes where it stopped (a tf.train.Saver built after build_train_op stores
+        them too: ae_train.py:81-82)."""
         self._modules = list(modules)
         self._global_step = global_step
+        self._train_op = train_op
 
     def variables(self):
         out = {}
@@ -227,6 +285,8 @@ class Saver(object):
                 out.update(m.get_weights())
         if self._global_step is not None:
             out[self._global_step.name] = self._global_step.value()
+        if self._train_op is not None:
+            out.update(self._train_op.optimizer_variables())
         return out
 
     def save(self, session, save_path, global_step=None):
@@ -275,6 +335,9 @@ class Saver(object):
                 m.load_weights(weights, strict=strict)
         if self._global_step is not None and self._global_step.name in weights:
             self._global_step._host = np.asarray(weights[self._global_step.name], dtype=np.int64)
+        if self._train_op is not None and session is not None:
+            gs = int(weights[self._global_step.name]) if self._global_step is not None and self._global_step.name in weights else None
+            self._train_op.load_optimizer_variables(weights, session.device, global_step=gs)
 
 
 def restore_checkpoint(session, saver, ckpt_dir, at_step=None):

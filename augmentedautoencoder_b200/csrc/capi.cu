@@ -866,6 +866,37 @@ extern "C" int aae_trainer_destroy(aae_trainer* h) {
 
 extern "C" int64_t aae_trainer_global_step(const aae_trainer* h) { return h ? h->step : -1; }
 
+// Adam slots of one variable pair (kernel, bias): m = TF's "<var>/Adam", v = "<var>/Adam_1".  get: dir = 0, set: dir = 1.
+static int trainer_state_io(aae_trainer* h, int which, int layer, float* km, float* kv, float* bm, float* bv, int dir, void* stream) {
+  AAE_REQUIRE(h != nullptr && (which == 0 || which == 1), "bad arguments");
+  std::vector<ParamGrad>& ks = which == 0 ? h->enc_k : h->dec_k;
+  std::vector<ParamGrad>& bs = which == 0 ? h->enc_b : h->dec_b;
+  AAE_REQUIRE(layer >= 0 && layer < (int)ks.size(), "layer %d out of range", layer);
+  DeviceGuard g(h->enc->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  struct { float* host; float* dev; size_t n; } io[4] = {{km, ks[layer].m.p, ks[layer].n}, {kv, ks[layer].v.p, ks[layer].n},
+                                                          {bm, bs[layer].m.p, bs[layer].n}, {bv, bs[layer].v.p, bs[layer].n}};
+  for (auto& t : io)
+    if (t.host) AAE_TRY(dir ? copy_any(t.dev, t.host, t.n * sizeof(float), s) : copy_any(t.host, t.dev, t.n * sizeof(float), s));
+  AAE_CUDA_OK(cudaStreamSynchronize(s));
+  return AAE_OK;
+}
+
+extern "C" int aae_trainer_get_state(aae_trainer* h, int which, int layer, float* kernel_m_any, float* kernel_v_any, float* bias_m_any,
+                                     float* bias_v_any, void* stream) {
+  return trainer_state_io(h, which, layer, kernel_m_any, kernel_v_any, bias_m_any, bias_v_any, 0, stream);
+}
+extern "C" int aae_trainer_set_state(aae_trainer* h, int which, int layer, const float* kernel_m_any, const float* kernel_v_any,
+                                     const float* bias_m_any, const float* bias_v_any, void* stream) {
+  return trainer_state_io(h, which, layer, const_cast<float*>(kernel_m_any), const_cast<float*>(kernel_v_any), const_cast<float*>(bias_m_any),
+                          const_cast<float*>(bias_v_any), 1, stream);
+}
+extern "C" int aae_trainer_set_global_step(aae_trainer* h, int64_t step) {
+  AAE_REQUIRE(h != nullptr && step >= 0, "bad arguments");
+  h->step = step;      // the bias correction of the next update uses t = step + 1, as after `step` updates
+  return AAE_OK;
+}
+
 extern "C" int aae_trainer_profile(aae_trainer* h, int enable, float* phase_ms_out, int capacity) {
   AAE_REQUIRE(h != nullptr, "trainer handle is null");
   DeviceGuard g(h->enc->device);

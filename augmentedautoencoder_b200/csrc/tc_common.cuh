@@ -215,23 +215,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
-// Multicast variants for clusters of two CTA pairs that share the B operand: the box lands at the same offset in every CTA
-// of `cta_mask`, and each destination's bytes complete on the barrier (same offset, peer bit cleared) of ITS pair's leader.
-__device__ __forceinline__ void tma_load_2d_2sm_mcast(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
-// commit with an explicit destination mask (bit i = CTA rank i of the cluster)
-__device__ __forceinline__ void umma_commit_2sm_mask(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
-
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand in the 128-byte-swizzle canonical layout:
 //   rows of 64 fp16 (128 B), 8-row groups 1024 B apart (SBO), TMA-written with CU_TENSOR_MAP_SWIZZLE_128B.

@@ -450,150 +450,6 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   }
 }
 
-// ------------------------------------------------------------------------------------------------- persistent kernel, cluster of two pairs
-// EXPERIMENTAL (AAE_TC_MCAST=1, off by default, not yet measured): clusters of four CTAs = two CTA pairs working on four
-// consecutive 128-row M tiles of the same N tile.  The pairs share the weight tile: every CTA fetches only a QUARTER of it
-// (64 rows) and multicasts that box to the CTA holding the same half in the other pair, so the L2 -> SM traffic per K chunk
-// drops from 32 KB to 24 KB per CTA -- the pair kernel sits on that fabric's ceiling.  A ring stage of a
-// CTA is written by its own producer and by its partner's, so a stage is free only when BOTH pairs' MMAs have consumed it:
-// the stage-free commit of each issuer goes to all four CTAs and the barrier counts two arrivals.
-template <int STAGES, int KCH>
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(TC_THREADS, 1)
-tc_gemm4p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const TcGemmParams p,
-                 const TcTileSched sch) {
-  using S = TcSmem2<STAGES, KCH>;
-  constexpr int N_TILE = 256;
-  constexpr int Q_BYTES = 64 * KCH * 2;                       // one weight quarter: 64 rows x KCH fp16
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();                   // 0..3; pairs (0,1) and (2,3)
-  const bool leader = (rank & 1u) == 0;
-  const int half = (int)(rank & 1u), quarter = (int)(rank >> 1);
-  const uint16_t pair_mask = (uint16_t)(3u << (rank & 2u));  // this CTA's pair
-  const uint16_t half_mask = half ? (uint16_t)0xA : (uint16_t)0x5;   // the two CTAs that hold this half of the weight tile
-  const int n_epi_warps = ((int)blockDim.x >> 5) - 4;
-  const int total_iters = p.taps * p.chunks_per_tap;
-  const int m_quads = (sch.m_pairs + 1) >> 1;
-  const int n_tiles_total = m_quads * sch.n_tiles * sch.splits;
-  const int first_tile = (int)(blockIdx.x >> 2), tile_step = (int)(gridDim.x >> 2);
-
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo); }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
-    mbar_init(tmem_full_bar, 1);
-    mbar_init(tmem_empty_bar, 2 * n_epi_warps);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc_2sm<512>(tmem_ptr);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const int hw = p.OH * p.OW;
-      int g = 0;
-      for (int t = first_tile; t < n_tiles_total; t += tile_step) {
-        const int mq = t % m_quads, r = t / m_quads, ny = r % sch.n_tiles, z = r / sch.n_tiles;
-        const int m0 = (mq * 4 + (int)rank) * 128, n0 = ny * N_TILE;
-        const int b0 = m0 / hw, rem = m0 - b0 * hw;
-        const int oh0 = rem / p.OW, ow0 = rem - oh0 * p.OW;
-        const int it_begin = z * p.iters_per_split, it_end = min(total_iters, it_begin + p.iters_per_split);
-        for (int it = it_begin; it < it_end; ++it, ++g) {
-          const int s = g % STAGES;
-          mbar_wait(&empty_bar[s], (((uint32_t)(g / STAGES)) & 1u) ^ 1u);   // both pairs are done with this stage (here AND in the partner CTA)
-          const int tap = it / p.chunks_per_tap, cc = it - tap * p.chunks_per_tap;
-          uint8_t* st = smem + s * S::STAGE_BYTES;
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);
-          const uint32_t lb = leader_bar_addr(&full_bar[s]);
-          const int c0 = p.tap_ch[tap] + cc * KCH;
-          const int x = ow0 + p.tap_dj[tap], y = oh0 + p.tap_di[tap];
-          tma_load_4d_2sm(st, &tm_a_hi, lb, c0, x, y, b0);
-          tma_load_4d_2sm(st + S::T_BYTES, &tm_a_lo, lb, c0, x, y, b0);
-          const int kcol = it * KCH, wrow = n0 + half * 128 + quarter * 64;
-          tma_load_2d_2sm_mcast(st + 2 * S::T_BYTES + quarter * Q_BYTES, &tm_w_hi, lb, kcol, wrow, half_mask);
-          tma_load_2d_2sm_mcast(st + 3 * S::T_BYTES + quarter * Q_BYTES, &tm_w_lo, lb, kcol, wrow, half_mask);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(256, N_TILE, 0);
-      int g = 0, tl = 0;
-      for (int t = first_tile; t < n_tiles_total; t += tile_step, ++tl) {
-        const int z = (t / m_quads) / sch.n_tiles;
-        const int it_begin = z * p.iters_per_split, it_end = min(total_iters, it_begin + p.iters_per_split);
-        if (tl > 0) {
-          mbar_wait(tmem_empty_bar, (uint32_t)(tl - 1) & 1u);
-          tc_fence_after();
-        }
-        for (int it = it_begin, i = 0; it < it_end; ++it, ++i, ++g) {
-          const int s = g % STAGES;
-          mbar_wait(&full_bar[s], ((uint32_t)(g / STAGES)) & 1u);
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
-          const uint64_t a_hi = KCH == 64 ? make_sw128_kmajor_desc(st) : make_sw64_kmajor_desc(st);
-          const uint64_t a_lo = KCH == 64 ? make_sw128_kmajor_desc(st + S::T_BYTES) : make_sw64_kmajor_desc(st + S::T_BYTES);
-          const uint64_t w_hi = KCH == 64 ? make_sw128_kmajor_desc(st + 2 * S::T_BYTES) : make_sw64_kmajor_desc(st + 2 * S::T_BYTES);
-          const uint64_t w_lo = KCH == 64 ? make_sw128_kmajor_desc(st + 3 * S::T_BYTES) : make_sw64_kmajor_desc(st + 3 * S::T_BYTES);
-#pragma unroll
-          for (int k = 0; k < KCH / 16; ++k) {
-            const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
-            umma_f16_2sm(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_hi, k), idesc, first);
-            umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, first);
-            umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
-          }
-          umma_commit_2sm_mask(&empty_bar[s], (uint16_t)0xF);   // frees the stage in all four CTAs (one of the two arrivals each waits for)
-        }
-        umma_commit_2sm_mask(tmem_full_bar, pair_mask);
-      }
-    }
-  } else if (warp >= 4) {
-    const int q = warp & 3, grp = (warp - 4) >> 2, epi_groups = n_epi_warps >> 2;
-    const float unscale = p.amax_bits ? p.unscale * tc_dyn_unscale(__ldg(p.amax_bits)) : p.unscale;
-    const uint32_t empty_addr = leader_bar_addr(tmem_empty_bar);
-    int tl = 0;
-    for (int t = first_tile; t < n_tiles_total; t += tile_step, ++tl) {
-      const int mq = t % m_quads, r = t / m_quads, ny = r % sch.n_tiles, z = r / sch.n_tiles;
-      const int m0 = (mq * 4 + (int)rank) * 128, n0 = ny * N_TILE;
-      const TcRow row = tc_decode_row(p, m0 + q * 32 + lane);
-      mbar_wait(tmem_full_bar, (uint32_t)tl & 1u);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = grp; c < N_TILE / 32; c += epi_groups) {
-        uint32_t v[32], x[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
-        tmem_ld_wait();
-        const int n = n0 + c * 32;
-        if (!row.valid || n >= p.N) continue;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * unscale;
-        tc_store_chunk(p, row, n, f, z);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(empty_addr);
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_2sm<512>(tmem_base);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------- packing kernels
 namespace {
 
@@ -649,38 +505,6 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
   auto kern = tc_gemm2_kernel<STAGES, KCH>;
   AAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   static const bool persistent = getenv("AAE_TC_NOPERSIST") == nullptr;
-  static const bool mcast = getenv("AAE_TC_MCAST") != nullptr;
-  if (persistent && mcast && L.has_w4 && KCH == 32) {
-    TcTileSched sch;
-    sch.m_pairs = (int)((grid.x + 1) / 2); sch.n_tiles = (int)grid.y; sch.splits = (int)grid.z;
-    const int tiles = ((sch.m_pairs + 1) / 2) * sch.n_tiles * sch.splits;
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto qk = tc_gemm4p_kernel<STAGES, KCH>;
-    AAE_CUDA_OK(cudaFuncSetAttribute(qk, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    // clusters of four must sit inside one GPC: fewer than sms / 4 of them may be resident at once, and a persistent grid
-    // larger than that would run its tail as a second wave
-    static int quad_slots = 0;
-    if (quad_slots == 0) {
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(4u * (unsigned)std::max(1, sms / 4));
-      cfg.blockDim = dim3((unsigned)tc_block_threads());
-      cfg.dynamicSmemBytes = S::TOTAL;
-      cudaLaunchAttribute at;
-      at.id = cudaLaunchAttributeClusterDimension;
-      at.val.clusterDim.x = 4; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-      cfg.attrs = &at; cfg.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, qk, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = std::max(1, sms / 4); }
-      quad_slots = n;
-      if (getenv("AAE_TC_VERBOSE")) fprintf(stderr, "[tc] clusters of 4 resident at once: %d (of %d SMs / 4 = %d)\n", n, sms, sms / 4);
-    }
-    qk<<<dim3(4u * (unsigned)std::min(tiles, quad_slots)), tc_block_threads(), S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w4_hi, L.tm_w4_lo, L.gp, sch);
-    AAE_LAUNCH_OK();
-    return AAE_OK;
-  }
   if (persistent) {
     TcTileSched sch;
     sch.m_pairs = (int)((grid.x + 1) / 2); sch.n_tiles = (int)grid.y; sch.splits = (int)grid.z;
@@ -823,10 +647,6 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
         const uint32_t box2[2] = {(uint32_t)T.kch, 128};
         if ((st = make_tmap_f16(&T.tm_w2_hi, T.w_hi, 2, dims, strides, box2, 2 * T.kch)) != AAE_OK) break;
         if ((st = make_tmap_f16(&T.tm_w2_lo, T.w_lo, 2, dims, strides, box2, 2 * T.kch)) != AAE_OK) break;
-        const uint32_t box4[2] = {(uint32_t)T.kch, 64};      // weight quarters for the multicast variant
-        if ((st = make_tmap_f16(&T.tm_w4_hi, T.w_hi, 2, dims, strides, box4, 2 * T.kch)) != AAE_OK) break;
-        if ((st = make_tmap_f16(&T.tm_w4_lo, T.w_lo, 2, dims, strides, box4, 2 * T.kch)) != AAE_OK) break;
-        T.has_w4 = true;
       }
     }
     // ---- static GEMM parameters ----
@@ -1085,10 +905,6 @@ int tc_layer_setup_plain(TcLayer& T, int B, bool pair_ok, bool alloc_input) {
       const uint32_t box2[2] = {(uint32_t)T.kch, 128};
       if ((st = make_tmap_f16(&T.tm_w2_hi, T.w_hi, 2, dims, strides, box2, 2 * T.kch)) != AAE_OK) return st;
       if ((st = make_tmap_f16(&T.tm_w2_lo, T.w_lo, 2, dims, strides, box2, 2 * T.kch)) != AAE_OK) return st;
-      const uint32_t box4[2] = {(uint32_t)T.kch, 64};
-      if ((st = make_tmap_f16(&T.tm_w4_hi, T.w_hi, 2, dims, strides, box4, 2 * T.kch)) != AAE_OK) return st;
-      if ((st = make_tmap_f16(&T.tm_w4_lo, T.w_lo, 2, dims, strides, box4, 2 * T.kch)) != AAE_OK) return st;
-      T.has_w4 = true;
     }
   }
   return AAE_OK;

@@ -75,9 +75,7 @@ struct TcLayer {
   __half *w_hi = nullptr, *w_lo = nullptr;      // packed weights [out_c][taps*in_c]
   CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo;
   CUtensorMap tm_w2_hi, tm_w2_lo;               // weight tile halves (128 rows) for the CTA-pair kernel
-  CUtensorMap tm_w4_hi, tm_w4_lo;               // weight tile quarters (64 rows) for the multicast variant
   bool pair = false;
-  bool has_w4 = false;
   TcGemmParams gp;
   int n_tile;
   int kch;    // K chunk per pipeline stage: 64 (128-byte swizzle) or 32 (64-byte swizzle, 4 stages)

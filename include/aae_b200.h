@@ -202,6 +202,16 @@ AAE_API int aae_trainer_forward_backward(aae_trainer* h, const float* x_dev, con
 /* which: 0 = encoder, 1 = decoder; layer as in *_set_weights. */
 AAE_API int aae_trainer_get_grads(aae_trainer* h, int which, int layer, float* kernel_grad_any, float* bias_grad_any, void* stream);
 AAE_API int64_t aae_trainer_global_step(const aae_trainer* h);
+/* Optimizer state, so that a training run can be resumed from a checkpoint the way tf.train.Saver does (the reference's
+ * Saver stores every variable's Adam slots and the beta powers: auto_pose/ae/ae_train.py:82,111-115).  which / layer as in
+ * aae_trainer_get_grads; *_m = first moment (TF slot name "<var>/Adam"), *_v = second moment ("<var>/Adam_1"), same shapes
+ * as the variable; NULL pointers are skipped.  aae_trainer_set_global_step(h, n) makes the next update the (n+1)-th
+ * (bias correction with beta^(n+1), TF's beta1_power / beta2_power after n steps). */
+AAE_API int aae_trainer_get_state(aae_trainer* h, int which, int layer, float* kernel_m_any, float* kernel_v_any, float* bias_m_any,
+                                  float* bias_v_any, void* stream);
+AAE_API int aae_trainer_set_state(aae_trainer* h, int which, int layer, const float* kernel_m_any, const float* kernel_v_any,
+                                  const float* bias_m_any, const float* bias_v_any, void* stream);
+AAE_API int aae_trainer_set_global_step(aae_trainer* h, int64_t step);
 /* Per-phase device time of the last training step (cudaEvents on the launching stream; tensor-core trainer only):
  * phase_ms_out[0..6] = operand packs, forward + loss, wgrad GEMMs, dgrad GEMMs, glue (masks / bias sums / re-splits),
  * fp32 backward of the dense layers and of conv1, Adam.  Same enable/read contract as aae_encoder_profile; returns the

@@ -314,3 +314,37 @@ def test_range_guard_reports_overflow_instead_of_garbage(sess):
         sess.run(dec.x, {zin: zz * 1e4})
     dec.load_weights(dp)
     assert np.all(np.isfinite(sess.run(dec.x, {zin: zz})))
+
+
+def test_training_resumes_from_a_checkpoint_with_the_optimizer_state(sess, tmp_path):
+    """tf.train.Saver stores the Adam slots and beta powers beside the weights (ae_train.py:82,111-115), so a resumed run continues
+    exactly; a weights-only restore restarts the optimizer (zero moments, bias correction from t = 1)."""
+    from augmentedautoencoder_b200.ae import factory
+    from augmentedautoencoder_b200.ae.tf_checkpoint import read_tf_checkpoint
+    xb = torch.from_numpy(np.random.RandomState(11).rand(3, 128, 128, 3).astype(np.float32)).cuda()
+    yb = torch.from_numpy(np.random.RandomState(12).rand(3, 128, 128, 3).astype(np.float32)).cuda()
+    enc, dec, top, _, _ = _train_pair(1, 4)
+    for _ in range(2):
+        top.step_device(xb, yb)
+    saver = factory.Saver([enc, dec], global_step=top._ae.global_step, train_op=top)
+    path = saver.save_tf(sess, str(tmp_path / "checkpoints" / "chkpt"), global_step=2)
+    stored = read_tf_checkpoint(path)
+    assert "conv2d_1/kernel/Adam" in stored and "conv2d_1/kernel/Adam_1" in stored and "dense_1/bias/Adam" in stored
+    assert abs(float(stored["beta1_power"]) - 0.9 ** 3) < 1e-7 and abs(float(stored["beta2_power"]) - 0.999 ** 3) < 1e-7
+    assert np.abs(stored["conv2d_1/kernel/Adam"]).max() > 0 and stored["conv2d_1/kernel/Adam_1"].min() >= 0
+    l3 = float(top.step_device(xb, yb))
+    w3 = enc.get_weights()["conv2d_2/kernel"]
+    # full restore: same third step
+    enc2, dec2, top2, _, _ = _train_pair(1, 4)
+    factory.Saver([enc2, dec2], global_step=top2._ae.global_step, train_op=top2).restore(sess, path)
+    assert int(top2._ae.global_step.value()) == 2
+    l3b = float(top2.step_device(xb, yb))
+    assert abs(l3 - l3b) < 1e-6 * max(1.0, abs(l3)), (l3, l3b)
+    assert np.max(np.abs(enc2.get_weights()["conv2d_2/kernel"] - w3)) < 1e-7
+    assert int(top2._ae.global_step.value()) == 3
+    # weights-only restore: the loss of the next step is the same (same weights) but the update is not (fresh optimizer)
+    enc3, dec3, top3, _, _ = _train_pair(1, 4)
+    factory.Saver([enc3, dec3]).restore(sess, path)
+    l3c = float(top3.step_device(xb, yb))
+    assert abs(l3 - l3c) < 1e-6 * max(1.0, abs(l3))
+    assert np.max(np.abs(enc3.get_weights()["conv2d_2/kernel"] - w3)) > 1e-6
