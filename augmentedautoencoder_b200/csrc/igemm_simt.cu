@@ -6,6 +6,8 @@
 //
 // One kernel, three gather modes (common.cuh):  C[M,N] = sum_k A[m,k] * Bm[k,n]
 //   tile 128x128x16, 256 threads, 8x8 register micro-tile, register-prefetch double buffering.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace aae {
@@ -382,6 +384,17 @@ int launch_igemm(const IGemmParams& p, int mode, cudaStream_t stream) {
 int launch_splitk_reduce(const float* partials, int splits, int64_t MN, int N, const float* bias, int act, float* out,
                          cudaStream_t stream) {
   const int threads = 256;
+  // This small kernel sits between kernels that use ~200 KB of shared memory per CTA (the dense GEMM before it, the fused match
+  // after it).  Asking for the same carveout avoids an L1/shared-memory reconfiguration of every SM on both sides
+  // (AAE_NO_CARVEOUT_HINT=1 leaves the default, for A/B measurements).
+  static const bool hinted = [] {
+    if (getenv("AAE_NO_CARVEOUT_HINT") == nullptr) {
+      cudaFuncSetAttribute(splitk_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(splitk_reduce4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    return true;
+  }();
+  (void)hinted;
   const bool aligned = ((uintptr_t)partials % 16 == 0) && ((uintptr_t)out % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0);
   if (MN % 4 == 0 && N % 4 == 0 && aligned && MN >= (1 << 20))   // small outputs: keep one thread per element for parallelism
     splitk_reduce4_kernel<<<(unsigned)ceil_div(MN / 4, threads), threads, 0, stream>>>(reinterpret_cast<const float4*>(partials), splits, MN / 4, N / 4,

@@ -395,8 +395,9 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_const
       const int row = mq * 128 + r;
       cp_async_16(stg + r * 512 + ((lane ^ (r & 31)) << 4), z + (long long)(row < B ? row : 0) * 128 + lane * 4, row < B);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");      // one group per round: round 1's rows keep arriving while round 0 is converted
   }
-  cp_async_wait_all();
+  if (MQ == 2) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -408,6 +409,10 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_const
   //      (lane = query, column c = K elements 2c, 2c+1; Q_hi at columns [mq*128, +64), Q_lo at [mq*128+64, +64)).
 #pragma unroll
   for (int mq = 0; mq < MQ; ++mq) {
+    if (mq == 1) {                                   // round 1's rows: this thread's copies have landed; the barrier makes everybody's visible
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
     const int q = warp & 3, half = warp >> 2, r = q * 32 + lane;
     const uint8_t* src = e_smem + (2 - mq) * MT_STAGE_BYTES + r * 512;
     float4 mine[16];

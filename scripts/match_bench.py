@@ -4,8 +4,9 @@ optional in-kernel clock trace.
     python scripts/match_bench.py [--rows 92232] [--batches 1,32,128,129,256] [--prec 1] [--k 1] [--upright] [--no-flush]
     AAE_MATCH_TRACE=1 python scripts/match_bench.py --batches 1,256 --iters 3      # per-phase clock64 trace of CTA 0 on stderr
 
-flush (default): a 256 MiB memset precedes every call, so the codebook comes from HBM and the queued launch hides the CPU
-launch latency; --no-flush times back-to-back calls with an idle GPU in between (adds ~12 us of launch latency).
+flush (default): a 256 MiB memset and then a 256 MiB read precede every call, so the codebook comes from HBM, the L2 holds
+clean lines (a memset alone leaves 126 MB of dirty lines whose write-back shares HBM with the timed kernel: --dirty-flush)
+and the queued launch hides the CPU launch latency; --no-flush times back-to-back calls with an idle GPU in between (adds ~12 us of launch latency).
 """
 import argparse
 import os
@@ -26,6 +27,7 @@ ap.add_argument("--prec", type=int, default=1)
 ap.add_argument("--k", type=int, default=1)
 ap.add_argument("--upright", action="store_true")
 ap.add_argument("--no-flush", action="store_true")
+ap.add_argument("--dirty-flush", action="store_true", help="memset only: leaves 126 MB of dirty lines in L2 whose write-back competes with the timed kernel")
 ap.add_argument("--iters", type=int, default=40)
 ap.add_argument("--hbm-gbs", type=float, default=6576.1)
 args = ap.parse_args()
@@ -44,12 +46,15 @@ cb = Codebook(enc, DS(), True, max_batch=256, precision=args.prec)
 E = np.random.RandomState(7).standard_normal((N, 128))
 cb.embedding_normalized.assign((E / np.linalg.norm(E, axis=1, keepdims=True)).astype(np.float32))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+clean = torch.zeros(64 << 20, dtype=torch.int32, device="cuda")          # 256 MiB read after the memset: L2 ends up full of CLEAN lines
 for B in [int(b) for b in args.batches.split(",")]:
     z = torch.randn(B, 128, device="cuda")
     ts = []
     for it in range(args.iters):
         if not args.no_flush:
             flush.zero_()
+            if not args.dirty_flush:
+                clean.sum()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         cb.match_device(z, k=args.k, upright=args.upright)
