@@ -43,6 +43,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    wanted = {os.path.basename(src)[:-3] + ".o" for src in srcs}
+    for f in os.listdir(objdir):                       # objects whose source is gone must neither be linked nor travel with the tree
+        if f.endswith(".o") and f not in wanted:
+            os.remove(os.path.join(objdir, f))
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")

@@ -2,7 +2,7 @@
 """bench.py -- pose queries/sec (encode + codebook NN) on 128x128 crops (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision simt|tc]
-                    [--workload infer|sharded|routed|train] [--batches-per-step M]
+                    [--workload infer|sharded|routed|train|process] [--batches-per-step M]
 
 infer (default, BASELINE.json configs[1]): one BATCH = 256 synthetic uint8 crops through the hot path: conv encoder -> latent
     -> fused L2-normalise + cosine match against the 92 232-row codebook -> (score, index) per crop.  One "step" = M (default
@@ -16,6 +16,7 @@ sharded (configs[4]): one 368 928-row codebook row-sharded over the ranks; per b
 routed (configs[3]): 8 objects = 8 (encoder, codebook) pairs spread over the ranks, batch = 1024 mixed crops routed by class,
     one all-reduce combines the per-crop results.
 train (configs[2]): one AAE training step at batch 64 on one GPU.
+process: AePoseEstimator.process on a 640x480 frame with 32 detections of two object classes.
 
 Printed JSON (rank 0, one line):
   value      whole-job queries/s with the crops already resident in HBM, device-timed (CUDA events, max over ranks)
@@ -662,6 +663,136 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+PROCESS_TRAIN_CFG = """[Paths]
+MODEL_PATH: /nonexistent.ply
+BACKGROUND_IMAGES_GLOB: /nonexistent/*.jpg
+[Dataset]
+MODEL: reconst
+H: 128
+W: 128
+C: 3
+RADIUS: 700
+RENDER_DIMS: (720, 540)
+K: [1075.65, 0, 720/2, 0, 1073.90, 540/2, 0, 0, 1]
+VERTEX_SCALE: 1
+ANTIALIASING: 1
+PAD_FACTOR: 1.2
+CLIP_NEAR: 10
+CLIP_FAR: 10000
+NOOF_TRAINING_IMGS: 10
+NOOF_BG_IMGS: 10
+[Augmentation]
+REALISTIC_OCCLUSION: False
+[Embedding]
+EMBED_BB: True
+MIN_N_VIEWS: 2562
+NUM_CYCLO: 36
+[Network]
+BATCH_NORMALIZATION: False
+AUXILIARY_MASK: False
+VARIATIONAL: 0
+LOSS: L2
+BOOTSTRAP_RATIO: 4
+NORM_REGULARIZE: 0
+LATENT_SPACE_SIZE: 128
+NUM_FILTER: [128, 256, 512, 512]
+STRIDES: [2, 2, 2, 2]
+KERNEL_SIZE_ENCODER: 5
+KERNEL_SIZE_DECODER: 5
+[Training]
+OPTIMIZER: Adam
+NUM_ITER: 30000
+BATCH_SIZE: 64
+LEARNING_RATE: 2e-4
+SAVE_INTERVAL: 10000
+[Queue]
+NUM_THREADS: 10
+QUEUE_SIZE: 50
+"""
+
+
+def run_process(args, rank, world, local_rank):
+    """The m3vision plugin call itself (auto_pose/m3_interface/ae_pose_estimator.py:133-232): one 640x480 frame with 32 detections of
+    two object classes -> 32 poses.  Host frame in, PoseEstimate list out; everything in between (frame upload, crop extraction,
+    encoder, codebook match, index read-back, vectorised pose lift) is inside the timed region.  `serial` repeats the frame with
+    one detection per call -- the reference's own pattern (one session.run per detection).  Not the headline metric."""
+    import tempfile
+
+    import torch
+    from augmentedautoencoder_b200 import _lib, build_ext
+    build_ext.build()
+    torch.cuda.set_device(local_rank)
+    from augmentedautoencoder_b200.m3_interface.ae_pose_estimator import AePoseEstimator
+    from augmentedautoencoder_b200.m3_interface.m3_interfaces import BoundingBox
+    lib = _lib.lib()
+    D = 32
+    with tempfile.TemporaryDirectory() as tmp:
+        os.environ["AE_WORKSPACE_PATH"] = os.path.join(tmp, "ws")
+        rng = np.random.RandomState(5)
+        for name, seed in (("obj_a", 1), ("obj_b", 2)):
+            d = os.path.join(tmp, "ws", "experiments", "grp", name)
+            os.makedirs(os.path.join(d, "checkpoints"))
+            open(os.path.join(d, name + ".cfg"), "w").write(PROCESS_TRAIN_CFG)
+            wrng = np.random.RandomState(40 + seed)
+            ckpt = {}
+            cin = 3
+            for i, f in enumerate((128, 256, 512, 512)):
+                lim = np.sqrt(6.0 / (25 * cin + 25 * f))
+                base = name + ("/conv2d" if i == 0 else "/conv2d_%d" % i)
+                ckpt[base + "/kernel"] = wrng.uniform(-lim, lim, (5, 5, cin, f)).astype(np.float32)
+                ckpt[base + "/bias"] = np.zeros(f, np.float32)
+                cin = f
+            lim = np.sqrt(6.0 / (32768 + 128))
+            ckpt[name + "/dense/kernel"] = wrng.uniform(-lim, lim, (32768, 128)).astype(np.float32)
+            ckpt[name + "/dense/bias"] = np.zeros(128, np.float32)
+            ckpt[name + "/embedding_normalized"] = unit_rows(wrng, N_ROWS)
+            ckpt[name + "/embed_obj_bbs_var"] = np.stack([wrng.randint(200, 400, N_ROWS), wrng.randint(100, 300, N_ROWS), wrng.randint(60, 200, N_ROWS),
+                                                          wrng.randint(60, 200, N_ROWS)], 1).astype(np.int32)
+            np.savez(os.path.join(d, "checkpoints", "chkpt-30000.npz"), **ckpt)
+        cfg = os.path.join(tmp, "m3.cfg")
+        open(cfg, "w").write("[methods]\nobject_pose_estimator = auto_pose\n[auto_pose]\ngpu_memory_fraction = 0.5\ncolor_format = bgr\n"
+                             "color_data_type = np.float32\ndepth_data_type = np.float32\nclass_2_encoder = {1:'grp/obj_a', 5:'grp/obj_b'}\n"
+                             "camPose = False\nupright = False\ntopk = 1\npose_visualization = False\n")
+        est = AePoseEstimator(cfg)
+        frame = rng.randint(0, 256, (480, 640, 3), dtype=np.uint8)
+        K = np.array([[572.4114, 0, 325.2611], [0, 573.57043, 242.04899], [0, 0, 1]])
+        dets = []
+        for i in range(D):
+            x0, y0 = rng.uniform(0.0, 0.6), rng.uniform(0.0, 0.6)
+            dets.append(BoundingBox(x0, y0, x0 + rng.uniform(0.1, 0.35), y0 + rng.uniform(0.1, 0.35), {1 if i % 2 == 0 else 5: 0.9}))
+        for _ in range(max(args.warmup, 3)):
+            poses = est.process(dets, frame, K)
+        assert len(poses) == D
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        n_frames = max(50, args.steps * 10)
+        torch.cuda.synchronize()
+        l0 = lib.aae_launch_count()
+        t0 = time.perf_counter()
+        for _ in range(n_frames):
+            poses = est.process(dets, frame, K)
+        t_batched = time.perf_counter() - t0
+        launches = int(lib.aae_launch_count() - l0)
+        n_serial = max(5, n_frames // 10)
+        t0 = time.perf_counter()
+        for _ in range(n_serial):
+            for det in dets:
+                est.process([det], frame, K)
+        t_serial = time.perf_counter() - t0
+        clocks = sampler.finish()
+        print(json.dumps({"metric": "poses/sec through AePoseEstimator.process (640x480 frame, 32 detections, 2 object classes)",
+                          "value": D * n_frames / t_batched, "unit": "poses/s", "n_gpus": 1, "steps": n_frames, "warmup": max(args.warmup, 3),
+                          "ms_per_step": 1e3 * t_batched / n_frames, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32 via split-fp16 tensor-core products (3x, fp32 accumulate)", "data": "synthetic",
+                          "config": {"workload": "SURVEY 8f N3: AePoseEstimator.process, one call per frame (all detections of a class in one batch)",
+                                     "detections_per_frame": D, "frame": "640x480x3 uint8 host array"},
+                          "frames_per_s": n_frames / t_batched,
+                          "e2e": {"value": D * n_frames / t_batched, "unit": "poses/s", "h2d_bytes_per_step": 480 * 640 * 3 + D * 16, "d2h_bytes_per_step": D * 4},
+                          "serial_one_detection_per_call": {"value": D * n_serial / t_serial, "unit": "poses/s",
+                                                            "note": "the reference's calling pattern (ae_pose_estimator.py:143-170: one session.run per detection)"},
+                          "gpu_launches": launches, "launches_per_frame": launches / n_frames, "clocks": clocks, "cpu_baseline": None, "roofline": None}))
+
+
 def run_train(args, rank, world, local_rank):
     """BASELINE.json configs[2]: AAE training step (encode + decode + bootstrapped L2 + backward + TF-Adam), batch 64, one GPU.
     Not the headline metric: an extra line for the results table (python bench.py --workload train)."""
@@ -768,7 +899,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-collective-workloads", action="store_true")
     ap.add_argument("--batches-per-step", type=int, default=16)
-    ap.add_argument("--workload", default="infer", choices=["infer", "train", "sharded", "routed"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "sharded", "routed", "process"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -779,6 +910,9 @@ def main():
     elif args.workload == "train":
         if rank == 0:
             run_train(args, rank, world, local_rank)
+    elif args.workload == "process":
+        if rank == 0:
+            run_process(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 
