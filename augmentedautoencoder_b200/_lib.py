@@ -49,6 +49,7 @@ _SIGS = {
     "aae_topk_merge": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "aae_topk_merge_packed": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "aae_codebook_rows": (_L, [_P]),
+    "aae_launch_floor_probe": (_I, [_I, _I, _P]),
     "aae_decoder_create": (_I, [_I, C.POINTER(NetCfg), C.POINTER(_P)]),
     "aae_decoder_destroy": (_I, [_P]),
     "aae_decoder_set_weights": (_I, [_P, _I, _P, _P, _P]),

@@ -529,6 +529,12 @@ extern "C" int aae_codebook_destroy(aae_codebook* h) {
 
 extern "C" int64_t aae_codebook_rows(const aae_codebook* h) { return h ? h->n_rows : -1; }
 
+extern "C" int aae_launch_floor_probe(int device, int with_tmem, void* stream) {
+  AAE_TRY(check_device(device));
+  DeviceGuard g(device);
+  return tc_launch_floor_probe(device, with_tmem, (cudaStream_t)stream);
+}
+
 extern "C" int aae_l2_normalize(const float* z_dev, int batch, int latent, float* zq_out_dev, void* stream) {
   AAE_REQUIRE(z_dev != nullptr && zq_out_dev != nullptr && batch >= 1 && latent >= 1, "bad arguments");
   return launch_l2_normalize(z_dev, batch, latent, zq_out_dev, (cudaStream_t)stream);
@@ -1051,12 +1057,19 @@ static int trainer_fwd_bwd_tc(aae_trainer* h, const float* x, const float* y, in
     AAE_TRY(tc_train_unit_dgrad(P, u, B, s));
     pt.mark(4, s);
     const bool last = u + 1 == n_units;
-    // masked gradient of conv i-1's output (space-to-depth order, columns (cls, cin)); its column sums are conv i-1's bias gradient
-    AAE_TRY(tc_train_finish(P, u, last ? -1 : u + 1, B, last, false, h->enc_b[i - 1].g.p, s));
+    const int c1 = tc_train_conv1_unit(P);
+    // masked gradient of conv i-1's output (space-to-depth order, columns (cls, cin)); its column sums are conv i-1's bias gradient.
+    // The last unit's result is conv1's output gradient: (hi, lo) operand of the tensor-core conv1 wgrad, or fp32 for the SIMT one
+    AAE_TRY(tc_train_finish(P, u, last ? c1 : u + 1, B, last && c1 < 0, false, h->enc_b[i - 1].g.p, s));
   }
-  // conv1 (Cin = 3, K = 75): fp32 wgrad from the plain-layout gradient the last unit wrote
-  pt.mark(5, s);
-  AAE_TRY(conv_wgrad(h, E->conv[0], x, B, tc_train_f32_out(P), h->enc_k[0].g.p, s));
+  if (tc_train_conv1_unit(P) >= 0) {
+    pt.mark(2, s);
+    AAE_TRY(tc_train_conv1_wgrad(P, x, B, h->enc_k[0].g.p, s));
+  } else {
+    // conv1 (Cin = 3, K = 75): fp32 wgrad from the plain-layout gradient the last unit wrote
+    pt.mark(5, s);
+    AAE_TRY(conv_wgrad(h, E->conv[0], x, B, tc_train_f32_out(P), h->enc_k[0].g.p, s));
+  }
   pt.mark(6, s);   // closes the last phase; aae_train_step charges Adam to phase 6 and closes it with one more mark
   return AAE_OK;
 }

@@ -43,6 +43,8 @@ int tc_train_create(TcEncoder* enc, TcDecoder* dec, int max_batch, TcTrainPlan**
 void tc_train_destroy(TcTrainPlan* h);
 int tc_train_num_units(const TcTrainPlan* h);
 int tc_train_num_decoder_units(const TcTrainPlan* h);
+int tc_train_conv1_unit(const TcTrainPlan* h);   // index of the wgrad-only conv1 unit (target of the last tc_train_finish), or -1
+int tc_train_conv1_wgrad(TcTrainPlan* h, const float* x_dev, int B, float* dw_out, cudaStream_t s);
 void tc_train_unit_info(const TcTrainPlan* h, int u, int* is_enc, int* cin, int* cout, int* gh, int* gw, int* nd);
 float* tc_train_raw(TcTrainPlan* h);
 float* tc_train_f32_out(TcTrainPlan* h);
@@ -59,6 +61,7 @@ int tc_train_unpack_flat(TcTrainPlan* h, int B, float* out, cudaStream_t s);
 int tc_codebook_create(int device, const float* E_dev, int64_t n_rows, int latent, int num_cyclo, int max_batch, TcCodebook** out);
 void tc_codebook_destroy(TcCodebook* h);
 int tc_codebook_max_k();
+int tc_launch_floor_probe(int device, int with_tmem, cudaStream_t s);
 // fused normalise + scores + top-k (k <= tc_codebook_max_k()), optionally over every num_cyclo-th row only (upright)
 int tc_codebook_match(TcCodebook* h, const float* z_dev, int B, int64_t row_offset, int k, int upright, float* scores_out, int32_t* idx_out,
                       cudaStream_t s);

@@ -645,6 +645,21 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_const
   if (tr && threadIdx.x == 0) trace[3] = clock64();
 }
 
+// Measurement aid (aae_launch_floor_probe): the fixed cost of launching a grid shaped like the match kernel -- one CTA per SM, the
+// same dynamic shared memory (forces the same L1/shared carveout), optionally the same 512-column TMEM allocation -- that does nothing.
+__global__ void __launch_bounds__(256, 1) launch_floor_kernel(int tmem, unsigned int* sink) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tmem_ptr;
+  if (tmem) {
+    if (threadIdx.x < 32) tmem_alloc<512>(&tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem_ptr);
+  }
+  if (sink != nullptr && threadIdx.x == 0 && smem_raw[0] == 0xFF && blockIdx.x == 0xFFFFFFFFu) *sink = 1u;   // never true: keeps smem_raw referenced
+}
+
 // fp32 [n_rows][128] -> (hi, lo) fp16 [n_pad][128], scaled by 64; rows >= n_rows are zero
 __global__ void pack_codebook_kernel(const float* __restrict__ E, long long n_rows, long long n_pad, __half* __restrict__ hi,
                                      __half* __restrict__ lo) {
@@ -679,6 +694,19 @@ struct TcCodebook {
 constexpr int MT_KMAX = 8;
 
 int tc_codebook_max_k() { return MT_KMAX; }
+
+int tc_launch_floor_probe(int device, int with_tmem, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AAE_CUDA_OK(cudaFuncSetAttribute(launch_floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_TOTAL));
+    attr_set = true;
+  }
+  cudaDeviceProp prop;
+  AAE_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  launch_floor_kernel<<<std::min(prop.multiProcessorCount, 148), 256, MT_SMEM_TOTAL, s>>>(with_tmem, nullptr);
+  AAE_LAUNCH_OK();
+  return AAE_OK;
+}
 
 int tc_codebook_create(int device, const float* E_dev, int64_t n_rows, int latent, int num_cyclo, int max_batch, TcCodebook** out) {
   *out = nullptr;

@@ -606,6 +606,36 @@ inline unsigned ew_grid(long long n, int threads = 256) {
   return (unsigned)std::max<long long>(1, std::min<long long>(b, 148 * 16));
 }
 
+// First encoder layer (Cin = 3, K = 75): its weight gradient is a 1x1 wgrad GEMM over the im2col matrix of the input image.
+// x fp32 [B, H, W, 3] -> A (hi, lo) fp16 [B*OH*OW][128]: column k = (kh*5 + kw)*3 + c < 75 holds scale * x[b, 2oh - pad_t + kh, 2ow - pad_l + kw, c]
+// (zero outside the image), columns 75..127 are zero.  One thread per (pixel, 8-column group): 16-byte stores.
+__global__ void conv1_im2col_kernel(const float* __restrict__ x, long long pixels, int H, int W, int OH, int OW, int pad_t, int pad_l, float scale,
+                                    __half* __restrict__ hi, __half* __restrict__ lo) {
+  const long long total = pixels * 16;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long pix = idx >> 4;
+    const int g = (int)(idx & 15);
+    const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH);
+    const long long b = pix / ((long long)OW * OH);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      v[j] = 0.f;
+      if (k < 75) {
+        const int kh = k / 15, r = k - kh * 15, kw = r / 3, c = r - kw * 3;
+        const int ih = 2 * oh - pad_t + kh, iw = 2 * ow - pad_l + kw;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v[j] = __ldg(x + ((b * H + ih) * W + iw) * 3 + c) * scale;
+      }
+    }
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) split_f16x2(v[2 * t], v[2 * t + 1], hh[t], ll[t]);
+    *reinterpret_cast<uint4*>(hi + pix * 128 + g * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(lo + pix * 128 + g * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+  }
+}
+
 template <int N_TILE, int STAGES>
 int launch_wgrad(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& gh, const CUtensorMap& gl, const TcWgradParams& p, dim3 grid,
                  cudaStream_t s) {
@@ -663,6 +693,9 @@ struct TcTrainPlan {
   size_t partial_floats = 0;
   float* wm = nullptr;            // fp32 merged sub-pixel weights / padded merged gradient scratch
   size_t wm_floats = 0;
+  // conv1 (Cin = 3): wgrad-only unit appended after the encoder units (index c1, -1 = SIMT wgrad): X = im2col of the input image
+  int c1 = -1;
+  __half *c1_x_hi = nullptr, *c1_x_lo = nullptr;
 };
 
 static int make_wgrad_maps(TcUnit& U, int x_c_total, int x_bpad, int g_bpad) {
@@ -764,6 +797,26 @@ int tc_train_create(TcEncoder* enc, TcDecoder* dec, int max_batch, TcTrainPlan**
     h->units.push_back(U);
     st = add_unit(h->units.back(), F, 4 * F.in_c);
   }
+  if (st == AAE_OK && Le >= 1 && enc->cfg.in_c == 3 && enc->cfg.kernel_size == 5 && enc->layers[0].in_c == 128 && getenv("AAE_C1_WGRAD_SIMT") == nullptr) {
+    // dW1[75, 128] = sum over pixels of im2col(x)[pixel, :75]^T G1[pixel, :]: the same 1x1 wgrad GEMM as the tap-separable output layer
+    const TcLayer& F2 = enc->layers[0];                    // conv2: its (space-to-depth) input is conv1's output, 2*in_h x 2*in_w x in_c plain
+    const size_t n = (size_t)B * (2 * F2.in_h) * (2 * F2.in_w) * 128;
+    st = tc_dev_alloc((void**)&h->c1_x_hi, n * sizeof(__half));
+    if (st == AAE_OK) st = tc_dev_alloc((void**)&h->c1_x_lo, n * sizeof(__half));
+    if (st == AAE_OK) {
+      TcLayer Fx;                                          // stands for "the layer whose input is X": only in_hi/in_lo, BB and the tap tables are read
+      memset(&Fx.gp, 0, sizeof(Fx.gp));
+      Fx.in_hi = h->c1_x_hi; Fx.in_lo = h->c1_x_lo; Fx.BB = 1;
+      TcUnit U;
+      U.enc = true; U.cin = 128; U.cout = F2.in_c;
+      U.gh = 2 * F2.in_h; U.gw = 2 * F2.in_w; U.gN = F2.in_c; U.n_real = F2.in_c;
+      U.taps_w = 1; U.dg_taps = 1; U.sep = false; U.nd = 128;   // (no dgrad is ever run for this unit: the input image needs no gradient)
+      U.mask_hi = nullptr;
+      h->units.push_back(U);
+      st = add_unit(h->units.back(), Fx, 128);
+      if (st == AAE_OK) h->c1 = (int)h->units.size() - 1;
+    }
+  }
   part_max = (size_t)40 << 20;   // 160 MB of fp32 partials; wgrad split counts are clamped to fit
   if (st == AAE_OK) st = tc_dev_alloc((void**)&h->amax, 64 * sizeof(unsigned));
   if (st == AAE_OK) st = tc_dev_alloc((void**)&h->raw, raw_max * sizeof(float));
@@ -780,10 +833,12 @@ void tc_train_destroy(TcTrainPlan* h) {
   if (!h) return;
   for (auto& U : h->units) { cudaFree(U.dg.in_hi); cudaFree(U.dg.in_lo); cudaFree(U.dg.w_hi); cudaFree(U.dg.w_lo); }
   cudaFree(h->amax); cudaFree(h->raw); cudaFree(h->f32_out); cudaFree(h->partials); cudaFree(h->wm);
+  cudaFree(h->c1_x_hi); cudaFree(h->c1_x_lo);
   delete h;
 }
 
-int tc_train_num_units(const TcTrainPlan* h) { return (int)h->units.size(); }
+int tc_train_num_units(const TcTrainPlan* h) { return (int)h->units.size() - (h->c1 >= 0 ? 1 : 0); }   // conv units with a dgrad
+int tc_train_conv1_unit(const TcTrainPlan* h) { return h->c1; }
 int tc_train_num_decoder_units(const TcTrainPlan* h) { return h->n_dec; }
 float* tc_train_raw(TcTrainPlan* h) { return h->raw; }
 float* tc_train_f32_out(TcTrainPlan* h) { return h->f32_out; }
@@ -870,6 +925,21 @@ int tc_train_unit_wgrad(TcTrainPlan* h, int u, int B, float* dw_out, cudaStream_
   }
   compact_cols_kernel<<<ew_grid((long long)w.ep.M * U.n_real), 256, 0, s>>>(h->wm, w.ep.M, U.gN, U.n_real, dw_out);
   AAE_LAUNCH_OK();
+  return AAE_OK;
+}
+
+// dW of conv1 [75][cout] from the fp32 input image x [B, H, W, 3] and the unit's G (written by tc_train_finish(..., next = conv1 unit))
+int tc_train_conv1_wgrad(TcTrainPlan* h, const float* x_dev, int B, float* dw_out, cudaStream_t s) {
+  AAE_REQUIRE(h->c1 >= 0, "tc trainer: no tensor-core conv1 wgrad unit");
+  TcUnit& U = h->units[h->c1];
+  const aae_net_cfg& cfg = h->enc->cfg;
+  const long long pixels = (long long)B * U.gh * U.gw;
+  const int pad_t = std::max((U.gh - 1) * 2 + 5 - cfg.in_h, 0) / 2, pad_l = std::max((U.gw - 1) * 2 + 5 - cfg.in_w, 0) / 2;
+  conv1_im2col_kernel<<<ew_grid(pixels * 16), 256, 0, s>>>(x_dev, pixels, cfg.in_h, cfg.in_w, U.gh, U.gw, pad_t, pad_l, ACT_SCALE, h->c1_x_hi, h->c1_x_lo);
+  AAE_LAUNCH_OK();
+  AAE_REQUIRE((size_t)128 * U.gN <= h->wm_floats, "tc trainer: scratch too small for the conv1 wgrad");
+  AAE_TRY(tc_train_unit_wgrad(h, h->c1, B, h->wm, s));         // [128 im2col columns][cout]; rows 75.. are zero
+  AAE_CUDA_OK(cudaMemcpyAsync(dw_out, h->wm, (size_t)75 * U.gN * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return AAE_OK;
 }
 

@@ -48,6 +48,7 @@ class AePoseEstimator(PoseEstInterface):
             devices = list(range(max(n_dev, 1)))
         self.sess = Session(device=devices[0])
         self._sessions = {}
+        self._class_streams = {}   # one CUDA stream per object class (process() overlaps the classes)
         for i, (clas_name, experiment) in enumerate(self.class_2_encoder.items()):
             full_name = experiment.split('/')
             experiment_name = full_name.pop()
@@ -117,20 +118,31 @@ class AePoseEstimator(PoseEstInterface):
         pending = []
         frame_u8 = np.ascontiguousarray(color_img if color_img.dtype == np.uint8 else color_img.astype(np.uint8))
         frames = {}   # device -> the frame, uploaded once per GPU
-        for clas, items in jobs.items():  # launch every class' batch first (different GPUs run concurrently) ...
+        # Launch every class' batch first, each on ITS OWN stream: an object class is an independent (encoder, codebook) pair, and a
+        # handful of crops per class does not fill 148 SMs -- the classes' kernels overlap on one GPU and run in parallel on
+        # different GPUs.  Results are collected afterwards.
+        for clas, items in jobs.items():
             cb, sess = self.all_codebooks[clas], self._sessions[clas]
             dev = sess.device
             with torch.cuda.device(dev):
+                cur = torch.cuda.current_stream(dev)
                 if dev not in frames:
                     frames[dev] = torch.from_numpy(frame_u8).to(dev, non_blocking=True)
-                crops = self.extract_square_patches_device(frames[dev], [it[1] for it in items], self.pad_factors[clas],
-                                                           self.patch_sizes[clas])
-                _, idx = cb.nearest_idx_device(crops, k=1, upright=self._upright)
-            pending.append((clas, items, idx))
-        for clas, items, idx in pending:     # ... then collect
+                st = self._class_streams.get(clas)
+                if st is None:
+                    st = self._class_streams[clas] = torch.cuda.Stream(device=dev)
+                st.wait_stream(cur)                              # the frame upload (and whatever the caller queued before)
+                with torch.cuda.stream(st):
+                    crops = self.extract_square_patches_device(frames[dev], [it[1] for it in items], self.pad_factors[clas],
+                                                               self.patch_sizes[clas])
+                    _, idx = cb.nearest_idx_device(crops, k=1, upright=self._upright)
+                frames[dev].record_stream(st)
+            pending.append((clas, items, idx, st))
+        for clas, items, idx, st in pending:     # ... then collect
             cb, sess = self.all_codebooks[clas], self._sessions[clas]
-            idcs = idx.cpu().numpy().astype(np.int64)[:, 0]
-            cb._encoder.check_range(sess.device)
+            with torch.cuda.device(sess.device), torch.cuda.stream(st):
+                idcs = idx.cpu().numpy().astype(np.int64)[:, 0]
+                cb._encoder.check_range(sess.device)
             train_args = self.all_train_args[clas]
             K_train = np.array(eval(train_args.get('Dataset', 'K'))).reshape(3, 3)
             radius = train_args.getfloat('Dataset', 'RADIUS')

@@ -147,6 +147,10 @@ AAE_API int aae_topk_merge(const float* scores_dev, const int32_t* idx_dev, int 
 AAE_API int aae_topk_merge_packed(const void* packed_dev, int n_shards, int batch, int k,
                                   float* scores_out_dev, int32_t* idx_out_dev, void* stream);
 AAE_API int64_t aae_codebook_rows(const aae_codebook* h);
+/* Measurement aid: launches a kernel shaped like the fused match (one CTA per SM, the same 193 KB of dynamic shared memory, with
+ * with_tmem != 0 the same 512-column TMEM allocation) that does no work -- the fixed launch / carveout / allocation cost that every
+ * event-timed or ncu-timed figure of that kernel contains (scripts/match_bench.py --floor). */
+AAE_API int aae_launch_floor_probe(int device, int with_tmem, void* stream);
 /* Same contract as aae_encoder_profile; one stage: the whole fused match (k = 1). */
 AAE_API int aae_codebook_profile(aae_codebook* h, int enable, float* stage_ms_out, int capacity);
 

@@ -30,6 +30,7 @@ ap.add_argument("--no-flush", action="store_true")
 ap.add_argument("--dirty-flush", action="store_true", help="memset only: leaves 126 MB of dirty lines in L2 whose write-back competes with the timed kernel")
 ap.add_argument("--iters", type=int, default=40)
 ap.add_argument("--hbm-gbs", type=float, default=6576.1)
+ap.add_argument("--floor", action="store_true", help="also time a do-nothing kernel with the match kernel's launch shape (193 KB smem, 512 TMEM columns)")
 args = ap.parse_args()
 
 N = args.rows
@@ -47,6 +48,24 @@ E = np.random.RandomState(7).standard_normal((N, 128))
 cb.embedding_normalized.assign((E / np.linalg.norm(E, axis=1, keepdims=True)).astype(np.float32))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 clean = torch.zeros(64 << 20, dtype=torch.int32, device="cuda")          # 256 MiB read after the memset: L2 ends up full of CLEAN lines
+if args.floor:
+    import ctypes as C
+    from augmentedautoencoder_b200 import _lib
+    for with_tmem in (0, 1):
+        ts = []
+        for it in range(args.iters):
+            if not args.no_flush:
+                flush.zero_()
+                if not args.dirty_flush:
+                    clean.sum()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(_lib.lib().aae_launch_floor_probe(0, with_tmem, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        ts = sorted(ts[min(5, len(ts) - 1):])
+        print("launch floor (148 CTAs x 256 threads, 193 KB dynamic smem, tmem alloc=%d, no work): median %.1f us  min %.1f us" % (with_tmem, ts[len(ts) // 2], ts[0]))
 for B in [int(b) for b in args.batches.split(",")]:
     z = torch.randn(B, 128, device="cuda")
     ts = []
