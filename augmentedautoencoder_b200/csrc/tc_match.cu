@@ -701,9 +701,9 @@ int tc_launch_floor_probe(int device, int with_tmem, cudaStream_t s) {
     AAE_CUDA_OK(cudaFuncSetAttribute(launch_floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_TOTAL));
     attr_set = true;
   }
-  cudaDeviceProp prop;
-  AAE_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  launch_floor_kernel<<<std::min(prop.multiProcessorCount, 148), 256, MT_SMEM_TOTAL, s>>>(with_tmem, nullptr);
+  static int sms = 0;                                   // (cudaGetDeviceProperties costs milliseconds: never on a timed path)
+  if (sms == 0) AAE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  launch_floor_kernel<<<std::min(sms, 148), 256, MT_SMEM_TOTAL, s>>>(with_tmem, nullptr);
   AAE_LAUNCH_OK();
   return AAE_OK;
 }

@@ -799,8 +799,8 @@ int tc_train_create(TcEncoder* enc, TcDecoder* dec, int max_batch, TcTrainPlan**
   }
   if (st == AAE_OK && Le >= 1 && enc->cfg.in_c == 3 && enc->cfg.kernel_size == 5 && enc->layers[0].in_c == 128 && getenv("AAE_C1_WGRAD_SIMT") == nullptr) {
     // dW1[75, 128] = sum over pixels of im2col(x)[pixel, :75]^T G1[pixel, :]: the same 1x1 wgrad GEMM as the tap-separable output layer
-    const TcLayer& F2 = enc->layers[0];                    // conv2: its (space-to-depth) input is conv1's output, 2*in_h x 2*in_w x in_c plain
-    const size_t n = (size_t)B * (2 * F2.in_h) * (2 * F2.in_w) * 128;
+    const TcLayer& F2 = enc->layers[0];                    // conv2: in_h x in_w x in_c are the dims of conv1's output (stored space-to-depth)
+    const size_t n = (size_t)B * F2.in_h * F2.in_w * 128;
     st = tc_dev_alloc((void**)&h->c1_x_hi, n * sizeof(__half));
     if (st == AAE_OK) st = tc_dev_alloc((void**)&h->c1_x_lo, n * sizeof(__half));
     if (st == AAE_OK) {
@@ -809,7 +809,7 @@ int tc_train_create(TcEncoder* enc, TcDecoder* dec, int max_batch, TcTrainPlan**
       Fx.in_hi = h->c1_x_hi; Fx.in_lo = h->c1_x_lo; Fx.BB = 1;
       TcUnit U;
       U.enc = true; U.cin = 128; U.cout = F2.in_c;
-      U.gh = 2 * F2.in_h; U.gw = 2 * F2.in_w; U.gN = F2.in_c; U.n_real = F2.in_c;
+      U.gh = F2.in_h; U.gw = F2.in_w; U.gN = F2.in_c; U.n_real = F2.in_c;
       U.taps_w = 1; U.dg_taps = 1; U.sep = false; U.nd = 128;   // (no dgrad is ever run for this unit: the input image needs no gradient)
       U.mask_hi = nullptr;
       h->units.push_back(U);
