@@ -345,8 +345,7 @@ template <int MQ, int K>
 __global__ void __launch_bounds__(256, 1)
 tc_match2_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_constant__ CUtensorMap tm_e_lo, const float* __restrict__ z,
                  int B, int n_rows, int n_tiles, int idx_mul, long long row_offset, int k_out, unsigned long long* __restrict__ best,
-                 unsigned long long* __restrict__ lists, unsigned int* __restrict__ counter, unsigned int* __restrict__ tile_counter,
-                 float* __restrict__ scores_out,
+                 unsigned long long* __restrict__ lists, unsigned int* __restrict__ counter, float* __restrict__ scores_out,
                  int* __restrict__ idx_out, long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* e_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -357,24 +356,17 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_const
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
   __shared__ int s_is_last;
   __shared__ float s_part[MQ][2][128];
-  // tile index of this CTA's i-th tile (i mod 8; -1 = no more tiles): written by the producer before it arms / arrives on the
-  // stage's full barrier, read by the MMA issuer and the epilogue warps after their barrier waits
-  __shared__ int s_tile_seq[8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool tr = trace != nullptr && blockIdx.x == 0;
   if (tr && threadIdx.x == 0) trace[0] = clock64();
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   // ring stage of this CTA's i-th tile.  MQ = 2 swaps stages 1 and 2: stage 2 is the staging area of the FIRST prologue round
   // and is free (and refilled) one round earlier than stage 1.
   auto stage_of = [](int i) -> int { const int r = i % MT_STAGES; return MQ == 1 ? r : (r == 0 ? 0 : MT_STAGES - r); };
-  // The first MT_STAGES tiles of a CTA are static (blockIdx.x + i * gridDim.x: no atomic on the start-up path); every further tile
-  // is taken from a global counter, so that SMs which the memory system serves faster simply stream more tiles -- with a static
-  // split the CTAs of one launch finished up to 3.5 us apart (globaltimer) and the slowest one set the kernel time.
-  auto load_tile = [&](int i, int tile) {            // tile < 0: nothing left -- publish the sentinel and complete the barrier phase
+  auto load_tile = [&](int i) {
     const int s = stage_of(i);
-    s_tile_seq[i & 7] = tile;
-    if (tile < 0) { mbar_arrive(&e_full[s]); return; }
-    const int row0 = tile * MT_ROWS;
+    const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * MT_ROWS;
     uint8_t* st = e_smem + s * MT_STAGE_BYTES;
     mbar_arrive_expect_tx(&e_full[s], MT_STAGE_BYTES);
     tma_load_2d(st, &tm_e_hi, &e_full[s], 0, row0);
@@ -388,10 +380,7 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_const
     for (int s = 0; s < MT_STAGES; ++s) { mbar_init(&e_full[s], 1); mbar_init(&e_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_barrier_init();
-    for (int i = 0; i < kPrefetch; ++i) {                                 // the codebook stream starts here
-      const int t = (int)blockIdx.x + i * (int)gridDim.x;
-      load_tile(i, t < n_tiles ? t : -1);
-    }
+    for (int i = 0; i < kPrefetch && i < my_tiles; ++i) load_tile(i);     // the codebook stream starts here
   }
   if (warp == 2) tmem_alloc<512>(tmem_ptr);
 
@@ -460,39 +449,25 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_const
     tc_fence_after();
     // the round's staging stage is free: request the tile that lives there (MQ = 1: tile 2 -> stage 2; MQ = 2: tile 1 -> stage 2,
     // then tile 2 -> stage 1)
-    if (threadIdx.x == 0) {
-      const int t = (int)blockIdx.x + (kPrefetch + mq) * (int)gridDim.x;
-      load_tile(kPrefetch + mq, t < n_tiles ? t : -1);
-    }
+    if (threadIdx.x == 0 && kPrefetch + mq < my_tiles) load_tile(kPrefetch + mq);
   }
   if (tr && threadIdx.x == 0) trace[1] = clock64();
   constexpr int kIssued = kPrefetch + MQ;     // tiles requested so far (= MT_STAGES)
 
   if (warp == 0) {
     if (lane == 0) {
-      // (a CTA whose static tiles already ran past the table has published its sentinel and never gets here with work)
-      bool more = (int)blockIdx.x + (kIssued - 1) * (int)gridDim.x < n_tiles;
-      for (int i = kIssued; more; ++i) {
-        // the ticket is taken BEFORE waiting for the stage: the atomic's round trip hides behind the wait
-        const int t = MT_STAGES * (int)gridDim.x + (int)atomicAdd(tile_counter, 1u);
+      for (int i = kIssued; i < my_tiles; ++i) {
         const int s = stage_of(i);
         mbar_wait(&e_empty[s], ((uint32_t)(i / MT_STAGES) & 1u) ^ 1u);
-        more = t < n_tiles;
-        load_tile(i, more ? t : -1);
+        load_tile(i);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, MT_ROWS, 0);
-      for (int i = 0;; ++i) {
+      for (int i = 0; i < my_tiles; ++i) {
         const int s = stage_of(i);
         mbar_wait(&e_full[s], (uint32_t)(i / MT_STAGES) & 1u);
-        if (s_tile_seq[i & 7] < 0) {                 // no more tiles: hand the sentinel on to the epilogue warps
-          const int u = i * MQ, as = u & 1;
-          mbar_wait(&acc_empty[as], ((uint32_t)(u >> 1) & 1u) ^ 1u);
-          mbar_arrive(&acc_full[as]);
-          break;
-        }
         if (tr && i < 16) trace[16 + i * 8 + 0] = clock64();
         const uint32_t est = smem_u32(e_smem + s * MT_STAGE_BYTES);
 #pragma unroll 1
@@ -525,20 +500,14 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_const
     const int q = warp & 3;
     TopList<K> l0, l1;                       // one list per query block (named objects: the mq loop is rolled)
     l0.init(); l1.init();
-    for (int i = 0;; ++i) {
-      {
-        const int u0 = i * MQ;                       // the tile's first accumulator (or the sentinel) is ready
-        mbar_wait(&acc_full[u0 & 1], (uint32_t)(u0 >> 1) & 1u);
-      }
-      const int tile = s_tile_seq[i & 7];
-      if (tile < 0) break;
-      const int row0 = tile * MT_ROWS;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * MT_ROWS;
       const int nvalid = min(MT_ROWS, n_rows - row0);
 #pragma unroll 1
       for (int mq = 0; mq < MQ; ++mq) {
         const int u = i * MQ + mq, as = u & 1;
         TopList<K> cur = mq ? l1 : l0;
-        if (mq > 0) mbar_wait(&acc_full[as], (uint32_t)(u >> 1) & 1u);
+        mbar_wait(&acc_full[as], (uint32_t)(u >> 1) & 1u);
         tc_fence_after();
         if (tr && warp == 4 && lane == 0 && i < 16) trace[16 + i * 8 + 5 + mq] = clock64();
 #pragma unroll 1
@@ -671,7 +640,7 @@ tc_match2_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_const
         }
       }
     }
-    if (threadIdx.x == 0) { *counter = 0u; *tile_counter = 0u; }
+    if (threadIdx.x == 0) *counter = 0u;
   }
   if (tr && threadIdx.x == 0) trace[3] = clock64();
 }
@@ -761,10 +730,10 @@ int tc_codebook_create(int device, const float* E_dev, int64_t n_rows, int laten
   if (e == cudaSuccess) e = cudaMalloc(&h->e_lo, (size_t)h->n_pad * 128 * sizeof(__half));
   if (e == cudaSuccess) e = cudaMalloc(&h->best, 256 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&h->lists, (size_t)h->sm_count * cap_b * MT_KMAX * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMalloc(&h->counter, 2 * sizeof(unsigned int));   // [0] finished CTAs, [1] dynamic tile tickets
+  if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(unsigned int));
   if (e != cudaSuccess) { set_error("tc codebook alloc failed: %s", cudaGetErrorString(e)); tc_codebook_destroy(h); return AAE_ERR_OOM; }
   cudaMemset(h->best, 0, 256 * sizeof(unsigned long long));
-  cudaMemset(h->counter, 0, 2 * sizeof(unsigned int));
+  cudaMemset(h->counter, 0, sizeof(unsigned int));
   if (getenv("AAE_MATCH_TRACE")) { cudaMalloc(&h->trace, 768 * sizeof(long long)); cudaMemset(h->trace, 0, 768 * sizeof(long long)); }
   pack_codebook_kernel<<<1024, 256>>>(E_dev, n_rows, h->n_pad, h->e_hi, h->e_lo);
   g_launches.fetch_add(1);
@@ -847,11 +816,11 @@ int tc_codebook_match(TcCodebook* h, const float* z_dev, int B, int64_t row_offs
       if (nb > 128) tc_match_kernel<2><<<grid, 256, MT_SMEM_TOTAL, s>>>(th, tl, z, nb, n_rows, n_tiles, (long long)row_offset, h->best, h->counter, so, io, h->trace);
       else tc_match_kernel<1><<<grid, 256, MT_SMEM_TOTAL, s>>>(th, tl, z, nb, n_rows, n_tiles, (long long)row_offset, h->best, h->counter, so, io, h->trace);
     } else if (k == 1) {
-      if (nb > 128) tc_match2_kernel<2, 1><<<grid, 256, MT_SMEM_TOTAL, s>>>(th, tl, z, nb, n_rows, n_tiles, idx_mul, (long long)row_offset, 1, h->best, h->lists, h->counter, h->counter + 1, so, io, h->trace);
-      else tc_match2_kernel<1, 1><<<grid, 256, MT_SMEM_TOTAL, s>>>(th, tl, z, nb, n_rows, n_tiles, idx_mul, (long long)row_offset, 1, h->best, h->lists, h->counter, h->counter + 1, so, io, h->trace);
+      if (nb > 128) tc_match2_kernel<2, 1><<<grid, 256, MT_SMEM_TOTAL, s>>>(th, tl, z, nb, n_rows, n_tiles, idx_mul, (long long)row_offset, 1, h->best, h->lists, h->counter, so, io, h->trace);
+      else tc_match2_kernel<1, 1><<<grid, 256, MT_SMEM_TOTAL, s>>>(th, tl, z, nb, n_rows, n_tiles, idx_mul, (long long)row_offset, 1, h->best, h->lists, h->counter, so, io, h->trace);
     } else {
-      if (nb > 128) tc_match2_kernel<2, MT_KMAX><<<grid, 256, MT_SMEM_TOTAL, s>>>(th, tl, z, nb, n_rows, n_tiles, idx_mul, (long long)row_offset, k, h->best, h->lists, h->counter, h->counter + 1, so, io, h->trace);
-      else tc_match2_kernel<1, MT_KMAX><<<grid, 256, MT_SMEM_TOTAL, s>>>(th, tl, z, nb, n_rows, n_tiles, idx_mul, (long long)row_offset, k, h->best, h->lists, h->counter, h->counter + 1, so, io, h->trace);
+      if (nb > 128) tc_match2_kernel<2, MT_KMAX><<<grid, 256, MT_SMEM_TOTAL, s>>>(th, tl, z, nb, n_rows, n_tiles, idx_mul, (long long)row_offset, k, h->best, h->lists, h->counter, so, io, h->trace);
+      else tc_match2_kernel<1, MT_KMAX><<<grid, 256, MT_SMEM_TOTAL, s>>>(th, tl, z, nb, n_rows, n_tiles, idx_mul, (long long)row_offset, k, h->best, h->lists, h->counter, so, io, h->trace);
     }
     AAE_LAUNCH_OK();
   }
