@@ -228,22 +228,24 @@ class ObjectRouter:
         return self._exchange(len(class_ids), parts, crops_dev.device)
 
     def route_host(self, crops_host, class_ids, device):
-        """crops_host: the mixed batch in HOST memory (torch uint8 tensor [B,H,W,C], ideally pinned).  This rank gathers the
+        """crops_host: the mixed batch in HOST memory (numpy array or torch CPU tensor [B,H,W,C], uint8 or float32; ideally pinned).  This rank gathers the
         crops of its own classes into a pinned staging buffer and uploads only those (1/world of the batch on average) --
         not the whole batch on every rank.  Same return value as ``route``."""
         plan = self.plan(class_ids)
         n_own = sum(len(sel) for _, sel in plan)
         parts = []
         if n_own:
-            if self._stage is None or self._stage.shape[0] < n_own or self._stage.shape[1:] != crops_host.shape[1:]:
+            src = crops_host.numpy() if isinstance(crops_host, torch.Tensor) else np.ascontiguousarray(crops_host)
+            if self._stage is None or self._stage.shape[0] < n_own or tuple(self._stage.shape[1:]) != tuple(src.shape[1:]) or \
+                    self._stage.numpy().dtype != src.dtype:
                 cap = max(n_own, -(-len(class_ids) // max(1, self.world)) * 2)
-                self._stage = torch.empty((cap,) + tuple(crops_host.shape[1:]), dtype=crops_host.dtype,
+                self._stage = torch.empty((cap,) + tuple(src.shape[1:]), dtype=torch.from_numpy(src[:0]).dtype,
                                           pin_memory=torch.cuda.is_available() and device.type == "cuda")
             order_np = np.concatenate([sel for _, sel in plan])
             order = torch.from_numpy(order_np)
             # row gather on the host into the pinned staging buffer: one memcpy per crop (measured: 6 ms per 1024 crops, against
             # 7-1000 ms for torch.index_select / np.take depending on thread-pool and page-fault state)
-            src, dst = crops_host.numpy(), self._stage.numpy()
+            dst = self._stage.numpy()
             for j, i in enumerate(order_np):
                 dst[j] = src[i]
             own_dev = self._stage[:n_own].to(device, non_blocking=True)

@@ -132,6 +132,8 @@ def _router_case(rank, world):
     s, i = router.route(crops, cls)
     sh, ih = router.route_host(crops, cls, torch.device("cpu"))       # host routing: only the rank's own crops are touched
     assert torch.equal(s, sh) and torch.equal(i, ih)
+    sn, in_ = router.route_host(crops.numpy(), cls, torch.device("cpu"))    # a numpy batch works too
+    assert torch.equal(s, sn) and torch.equal(i, in_)
     n_own = sum(len(sel) for _, sel in router.plan(cls))
     assert n_own == sum(1 for c in cls if owner.get(int(c)) == rank) and n_own < len(cls)
     return s.numpy(), i.numpy()
