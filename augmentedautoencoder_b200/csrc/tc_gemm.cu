@@ -499,6 +499,37 @@ __global__ void unpack_act_kernel(const __half* __restrict__ hi, const __half* _
 // ------------------------------------------------------------------------------------------------- encoder plan
 namespace {
 
+// Split-K forward of a conv layer at small batch: the GEMM leaves fp32 partial sums [splits][M][N] (OUT_F32); this kernel folds
+// them in a fixed order and applies the layer's real epilogue -- bias, ReLU, range guard, (hi, lo) split, store in the next
+// layer's layout (tc_store_chunk's OUT_S2D_SPLIT / OUT_PLAIN_SPLIT branch).  One thread per (row, 8 columns).
+__global__ void __launch_bounds__(256) splitk_forward_finish_kernel(const float* __restrict__ partials, int splits, const TcGemmParams p) {
+  const long long groups = (long long)p.M * (p.N >> 3);
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(gi / (p.N >> 3)), n = (int)(gi - (long long)m * (p.N >> 3)) << 3;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* src = partials + (long long)m * p.N + n;
+    for (int sp = 0; sp < splits; ++sp, src += (long long)p.M * p.N) {
+      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    }
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = f[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+      if (p.relu == 1) v = fmaxf(v, 0.f);
+      amax = fmaxf(amax, fabsf(v));
+      f[j] = v * p.out_scale;
+    }
+    if (p.range_flag != nullptr && !(amax * p.out_scale < TC_F16_OVERFLOW)) atomicOr(p.range_flag, p.range_bit);
+    const TcRow r = tc_decode_row(p, m);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_f16x2(f[2 * j], f[2 * j + 1], hi[j], lo[j]);
+    *reinterpret_cast<uint4*>(p.out_hi + r.row_off + n) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(p.out_lo + r.row_off + n) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 template <int STAGES, int KCH>
 int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
   using S = TcSmem2<STAGES, KCH>;
@@ -701,6 +732,7 @@ void tc_encoder_destroy(TcEncoder* h) {
   if (!h) return;
   for (auto& T : h->layers) { cudaFree(T.in_hi); cudaFree(T.in_lo); cudaFree(T.w_hi); cudaFree(T.w_lo); }
   cudaFree(h->partials);
+  cudaFree(h->fwd_partials);
   cudaFree(h->dbg);
   cudaFree(h->range_flag);
   tc_conv1_destroy(h->conv1);
@@ -769,7 +801,42 @@ int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const
     const bool dense = (i + 1 == h->layers.size());
     T.gp.M = dense ? B : B * T.out_h * T.out_w;
     dim3 grid((unsigned)ceil_div(T.gp.M, 128), (unsigned)ceil_div(T.out_c, T.n_tile), dense ? (unsigned)h->dense_splits : 1u);
-    AAE_TRY(tc_launch_layer(T, grid, s));
+    // Small batches leave most SM pairs idle (conv4 at 32 crops: 16 tiles of 400 K iterations for 74 pairs): split K so that the
+    // persistent grid is covered, fold the fp32 partials and apply the real epilogue in splitk_forward_finish_kernel.
+    int splits = 1;
+    if (!dense && T.pair && T.gp.out_mode != OUT_F32 && getenv("AAE_TC_NO_FWD_SPLITK") == nullptr) {
+      const int tiles = (int)((grid.x + 1) / 2) * (int)grid.y, total_iters = T.gp.taps * T.gp.chunks_per_tap;
+      if (tiles * 2 <= 74) {
+        splits = std::min(74 / tiles, std::max(1, total_iters / 24));
+        const size_t per_split = (size_t)T.gp.M * T.gp.N;
+        if (per_split * (size_t)splits > h->fwd_partial_floats) {
+          const size_t want = std::min<size_t>(per_split * (size_t)splits, (size_t)32 << 20);     // at most 128 MB of partials
+          if (want > h->fwd_partial_floats) {
+            cudaFree(h->fwd_partials);
+            h->fwd_partials = nullptr; h->fwd_partial_floats = 0;
+            AAE_TRY(dev_alloc((void**)&h->fwd_partials, want * sizeof(float)));
+            h->fwd_partial_floats = want;
+          }
+          splits = (int)std::min<size_t>((size_t)splits, h->fwd_partial_floats / per_split);
+        }
+        splits = std::max(splits, 1);
+      }
+    }
+    if (splits > 1) {
+      TcLayer S = T;                                   // same operands and maps, partial sums out
+      const int total_iters = T.gp.taps * T.gp.chunks_per_tap;
+      S.gp.iters_per_split = (int)ceil_div(total_iters, splits);
+      splits = (int)ceil_div(total_iters, S.gp.iters_per_split);
+      S.gp.out_mode = OUT_F32;
+      S.gp.out_f32 = h->fwd_partials;
+      grid.z = (unsigned)splits;
+      AAE_TRY(tc_launch_layer(S, grid, s));
+      const long long groups = (long long)T.gp.M * (T.gp.N >> 3);
+      splitk_forward_finish_kernel<<<(unsigned)std::min<long long>(148 * 8, ceil_div(groups, 256)), 256, 0, s>>>(h->fwd_partials, splits, T.gp);
+      AAE_LAUNCH_OK();
+    } else {
+      AAE_TRY(tc_launch_layer(T, grid, s));
+    }
     if (dense) AAE_TRY(launch_splitk_reduce(h->partials, h->dense_splits, (int64_t)B * cfg.latent, cfg.latent, dense_b, ACT_NONE, z_out, s));
     tc_mark(h, s);
   }

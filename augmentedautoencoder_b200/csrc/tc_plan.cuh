@@ -90,6 +90,8 @@ struct TcEncoder {
   std::vector<TcLayer> layers;   // conv layers 1..L-1 followed by the dense layer
   int flat;
   float* partials = nullptr;     // dense split-K partials [splits, max_batch, latent]
+  float* fwd_partials = nullptr; // conv split-K partials of small-batch forwards [splits, M, N] (allocated on first use)
+  size_t fwd_partial_floats = 0;
   int dense_splits = 1;
   TcConv1* conv1 = nullptr;      // tensor-core first layer (when the geometry allows), else the fp32 SIMT kernel
   float* dbg = nullptr;          // fp32 view of an activation (tests)
