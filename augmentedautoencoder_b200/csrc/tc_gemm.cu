@@ -804,7 +804,8 @@ int tc_encoder_forward(TcEncoder* h, const void* crops, int src_u8, int B, const
     // Small batches leave most SM pairs idle (conv4 at 32 crops: 16 tiles of 400 K iterations for 74 pairs): split K so that the
     // persistent grid is covered, fold the fp32 partials and apply the real epilogue in splitk_forward_finish_kernel.
     int splits = 1;
-    if (!dense && T.pair && T.gp.out_mode != OUT_F32 && getenv("AAE_TC_NO_FWD_SPLITK") == nullptr) {
+    static const bool fwd_splitk = getenv("AAE_TC_NO_FWD_SPLITK") == nullptr;     // (A/B switch, read once)
+    if (!dense && T.pair && T.gp.out_mode != OUT_F32 && fwd_splitk) {
       const int tiles = (int)((grid.x + 1) / 2) * (int)grid.y, total_iters = T.gp.taps * T.gp.chunks_per_tap;
       if (tiles * 2 <= 74) {
         splits = std::min(74 / tiles, std::max(1, total_iters / 24));
