@@ -316,6 +316,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 
 struct TcTileSched {
   int m_pairs, n_tiles, splits;   // tiles = m_pairs * n_tiles * splits, each tile = 256 rows x 256 columns x one K range
+  int dbg;                        // TIMING EXPERIMENTS ONLY (AAE_TC_DEBUG, wrong results): 0 = production; 1/2 = that many products; 11 = one product AND only the hi tiles loaded
+  long long* trace;               // AAE_TC_TRACE: clock64 of CTA 0 for its first 96 chunks: [g*4+0] TMA issued, +1 full barrier seen by the MMA thread, +2 MMAs issued, +3 stage seen empty again
 };
 
 template <int STAGES, int KCH>
@@ -341,6 +343,11 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   const int n_tiles_total = sch.m_pairs * sch.n_tiles * sch.splits;
   const int first_tile = (int)(blockIdx.x >> 1), tile_step = (int)(gridDim.x >> 1);
 
+  if (sch.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    sch.trace[384] = clock64(); sch.trace[385] = (long long)gt;
+  }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -367,17 +374,20 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         for (int it = it_begin; it < it_end; ++it, ++g) {
           const int s = g % STAGES;
           mbar_wait(&empty_bar[s], (((uint32_t)(g / STAGES)) & 1u) ^ 1u);
+          if (sch.trace && blockIdx.x == 0 && g >= STAGES && g - STAGES < 96) sch.trace[(g - STAGES) * 4 + 3] = clock64();
           const int tap = it / p.chunks_per_tap, cc = it - tap * p.chunks_per_tap;
           uint8_t* st = smem + s * S::STAGE_BYTES;
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);
+          const bool hi_only = sch.dbg == 11;
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], hi_only ? S::STAGE_BYTES : 2 * S::STAGE_BYTES);
           const uint32_t lb = leader_bar_addr(&full_bar[s]);
           const int c0 = p.tap_ch[tap] + cc * KCH;
           const int x = ow0 + p.tap_dj[tap], y = oh0 + p.tap_di[tap];
           tma_load_4d_2sm(st, &tm_a_hi, lb, c0, x, y, b0);
-          tma_load_4d_2sm(st + S::T_BYTES, &tm_a_lo, lb, c0, x, y, b0);
+          if (!hi_only) tma_load_4d_2sm(st + S::T_BYTES, &tm_a_lo, lb, c0, x, y, b0);
           const int kcol = it * KCH;
           tma_load_2d_2sm(st + 2 * S::T_BYTES, &tm_w_hi, lb, kcol, n0 + (int)rank * 128);
-          tma_load_2d_2sm(st + 3 * S::T_BYTES, &tm_w_lo, lb, kcol, n0 + (int)rank * 128);
+          if (!hi_only) tma_load_2d_2sm(st + 3 * S::T_BYTES, &tm_w_lo, lb, kcol, n0 + (int)rank * 128);
+          if (sch.trace && blockIdx.x == 0 && g < 96) sch.trace[g * 4 + 0] = clock64();
         }
       }
     }
@@ -389,13 +399,16 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         const int z = (t / sch.m_pairs) / sch.n_tiles;
         const int it_begin = z * p.iters_per_split, it_end = min(total_iters, it_begin + p.iters_per_split);
         if (tl > 0) {                                           // both CTAs' epilogues have drained the previous accumulators
+          if (sch.trace && blockIdx.x == 0 && tl < 16) sch.trace[392 + tl * 4 + 0] = clock64();
           mbar_wait(tmem_empty_bar, (uint32_t)(tl - 1) & 1u);
           tc_fence_after();
+          if (sch.trace && blockIdx.x == 0 && tl < 16) sch.trace[392 + tl * 4 + 1] = clock64();
         }
         for (int it = it_begin, i = 0; it < it_end; ++it, ++i, ++g) {
           const int s = g % STAGES;
           mbar_wait(&full_bar[s], ((uint32_t)(g / STAGES)) & 1u);
           tc_fence_after();
+          if (sch.trace && blockIdx.x == 0 && g < 96) sch.trace[g * 4 + 1] = clock64();
           const uint32_t st = smem_u32(smem + s * S::STAGE_BYTES);
           const uint64_t a_hi = KCH == 64 ? make_sw128_kmajor_desc(st) : make_sw64_kmajor_desc(st);
           const uint64_t a_lo = KCH == 64 ? make_sw128_kmajor_desc(st + S::T_BYTES) : make_sw64_kmajor_desc(st + S::T_BYTES);
@@ -405,10 +418,11 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           for (int k = 0; k < KCH / 16; ++k) {
             const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
             umma_f16_2sm(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_hi, k), idesc, first);
-            umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, first);
-            umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
+            if (sch.dbg == 0 || sch.dbg == 2 || sch.dbg > 20) umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, first);
+            if (sch.dbg == 0 || sch.dbg > 20) umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
           }
           umma_commit_2sm(&empty_bar[s]);
+          if (sch.trace && blockIdx.x == 0 && g < 96) sch.trace[g * 4 + 2] = clock64();
         }
         umma_commit_2sm(tmem_full_bar);
       }
@@ -417,6 +431,8 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int q = warp & 3, grp = (warp - 4) >> 2, epi_groups = n_epi_warps >> 2;
     const float unscale = p.amax_bits ? p.unscale * tc_dyn_unscale(__ldg(p.amax_bits)) : p.unscale;
     const uint32_t empty_addr = leader_bar_addr(tmem_empty_bar);
+    const bool lean = tc_lean_epilogue_ok(p) && !(sch.dbg == 30);
+    const float floor_v = p.relu == 1 ? 0.f : -INFINITY;
     int tl = 0;
     for (int t = first_tile; t < n_tiles_total; t += tile_step, ++tl) {
       const int mp = t % sch.m_pairs, r = t / sch.m_pairs, ny = r % sch.n_tiles, z = r / sch.n_tiles;
@@ -424,23 +440,43 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       const TcRow row = tc_decode_row(p, m0 + q * 32 + lane);
       mbar_wait(tmem_full_bar, (uint32_t)tl & 1u);
       tc_fence_after();
+      if (sch.trace && blockIdx.x == 0 && threadIdx.x == 128 && tl < 16) sch.trace[392 + tl * 4 + 2] = clock64();
+      if (lean) {
 #pragma unroll 1
-      for (int c = grp; c < N_TILE / 32; c += epi_groups) {
-        uint32_t v[32], x[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
-        tmem_ld_wait();
-        const int n = n0 + c * 32;
-        if (!row.valid || n >= p.N) continue;
-        float f[32];
+        for (int c = grp; c < N_TILE / 32; c += epi_groups) {
+          uint32_t v[32], x[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
+          tmem_ld_wait();
+          const int n = n0 + c * 32;
+          if (!row.valid || n >= p.N) continue;
+          tc_store_chunk_lean(p, row, n, v, x, unscale, floor_v);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = grp; c < N_TILE / 32; c += epi_groups) {
+          uint32_t v[32], x[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
+          tmem_ld_wait();
+          const int n = n0 + c * 32;
+          if (!row.valid || n >= p.N) continue;
+          float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * unscale;
-        tc_store_chunk(p, row, n, f, z);
+          for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(x[j])) * unscale;
+          tc_store_chunk(p, row, n, f, z);
+        }
       }
       tc_fence_before();                                        // this warp's TMEM reads are complete
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(empty_addr);
+      if (sch.trace && blockIdx.x == 0 && threadIdx.x == 128 && tl < 16) sch.trace[392 + tl * 4 + 3] = clock64();
     }
+  }
+  if (sch.trace && blockIdx.x == 0 && threadIdx.x == 128) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    sch.trace[386] = clock64(); sch.trace[387] = (long long)gt;
   }
   tc_fence_before();
   cluster_sync_all();
@@ -539,6 +575,15 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
   if (persistent) {
     TcTileSched sch;
     sch.m_pairs = (int)((grid.x + 1) / 2); sch.n_tiles = (int)grid.y; sch.splits = (int)grid.z;
+    const char* dbg = getenv("AAE_TC_DEBUG");          // read per launch (scripts/ab_inproc.py)
+    sch.dbg = dbg ? atoi(dbg) : 0;
+    static long long* trace_dev = nullptr;
+    sch.trace = nullptr;
+    if (getenv("AAE_TC_TRACE")) {
+      if (!trace_dev) { cudaMalloc(&trace_dev, (96 * 4 + 8 + 64) * sizeof(long long)); }
+      cudaMemsetAsync(trace_dev, 0, (96 * 4 + 8 + 64) * sizeof(long long), s);
+      sch.trace = trace_dev;
+    }
     const int tiles = sch.m_pairs * sch.n_tiles * sch.splits;
     auto pk = tc_gemm2p_kernel<STAGES, KCH>;
     AAE_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -563,6 +608,20 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
     }
     pk<<<dim3(2u * (unsigned)std::min(tiles, pair_slots)), tc_block_threads(), S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w2_hi, L.tm_w2_lo, L.gp, sch);
     AAE_LAUNCH_OK();
+    if (sch.trace) {
+      long long t[96 * 4 + 8 + 64];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(t, sch.trace, sizeof(t), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[gemm2p trace] N=%d taps=%d chunks/tap=%d: chunk: issue | +full seen | +mma issued | next-use empty seen (clocks, relative to chunk 0 issue)\n", L.gp.N, L.gp.taps, L.gp.chunks_per_tap);
+      fprintf(stderr, "  CTA 0 (epilogue warp 4): %lld cycles in %lld ns -> SM clock %.0f MHz during this kernel\n", t[386] - t[384], t[387] - t[385],
+              1e3 * (double)(t[386] - t[384]) / (double)(t[387] - t[385]));
+      for (int tl = 0; tl < 15; ++tl)
+        fprintf(stderr, "  tile %2d: epilogue warp 4 sees accumulators at %8lld, done +%6lld | issuer waits for drained TMEM from %8lld for %6lld\n", tl,
+                t[392 + tl * 4 + 2] - t[384], t[392 + tl * 4 + 3] - t[392 + tl * 4 + 2], t[392 + tl * 4 + 0] - t[384], t[392 + tl * 4 + 1] - t[392 + tl * 4 + 0]);
+      for (int g = 0; g < 96; g += (g < 8 ? 1 : 16))
+        fprintf(stderr, "  g=%2d issue %7lld | full +%5lld | mma issued +%5lld | empty seen +%5lld\n", g, t[g * 4] - t[0], t[g * 4 + 1] - t[g * 4], t[g * 4 + 2] - t[g * 4],
+                t[g * 4 + 3] - t[g * 4]);
+    }
     return AAE_OK;
   }
   grid.x = (grid.x + 1) & ~1u;   // whole CTA pairs
@@ -656,9 +715,14 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
       const uint64_t C4 = 4ull * T.in_c, W2 = T.in_w / 2, H2 = T.in_h / 2;
       const uint64_t dims[4] = {C4, W2, H2, (uint64_t)B_pad};
       const uint64_t strides[3] = {C4 * 2, W2 * C4 * 2, H2 * W2 * C4 * 2};
-      const uint32_t box[4] = {(uint32_t)T.kch, (uint32_t)T.BW, (uint32_t)T.BH, (uint32_t)T.BB};
-      if ((st = make_tmap_f16(&T.tm_a_hi, T.in_hi, 4, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
-      if ((st = make_tmap_f16(&T.tm_a_lo, T.in_lo, 4, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
+      uint32_t box[4] = {(uint32_t)T.kch, (uint32_t)T.BW, (uint32_t)T.BH, (uint32_t)T.BB};
+      int swz = 2 * T.kch;
+      // HYPOTHESIS TEST ONLY (AAE_TC_DEBUG_BOX128=1, wrong results): the same bytes per stage fetched as 128-byte rows (64 channels x half
+      // the pixels) instead of 64-byte rows -- is the L2 -> SM path limited by requests rather than bytes?
+      const bool dbg128 = getenv("AAE_TC_DEBUG_BOX128") != nullptr && T.kch == 32;
+      if (dbg128) { box[0] = 64; if (T.BH >= 2) box[2] = T.BH / 2; else box[1] = T.BW / 2; swz = 128; }
+      if ((st = make_tmap_f16(&T.tm_a_hi, T.in_hi, 4, dims, strides, box, swz)) != AAE_OK) break;
+      if ((st = make_tmap_f16(&T.tm_a_lo, T.in_lo, 4, dims, strides, box, swz)) != AAE_OK) break;
     } else {
       const uint64_t dims[4] = {(uint64_t)T.in_c, 1, 1, (uint64_t)B_pad};
       const uint64_t strides[3] = {(uint64_t)T.in_c * 2, (uint64_t)T.in_c * 2, (uint64_t)T.in_c * 2};
@@ -675,9 +739,11 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
       if ((st = make_tmap_f16(&T.tm_w_lo, T.w_lo, 2, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
       T.pair = !dense && T.n_tile == 256 && T.out_c % 256 == 0 && getenv("AAE_TC_1CTA") == nullptr;
       if (T.pair) {
-        const uint32_t box2[2] = {(uint32_t)T.kch, 128};
-        if ((st = make_tmap_f16(&T.tm_w2_hi, T.w_hi, 2, dims, strides, box2, 2 * T.kch)) != AAE_OK) break;
-        if ((st = make_tmap_f16(&T.tm_w2_lo, T.w_lo, 2, dims, strides, box2, 2 * T.kch)) != AAE_OK) break;
+        uint32_t box2[2] = {(uint32_t)T.kch, 128};
+        int swz2 = 2 * T.kch;
+        if (getenv("AAE_TC_DEBUG_BOX128") != nullptr && T.kch == 32) { box2[0] = 64; box2[1] = 64; swz2 = 128; }   // see above
+        if ((st = make_tmap_f16(&T.tm_w2_hi, T.w_hi, 2, dims, strides, box2, swz2)) != AAE_OK) break;
+        if ((st = make_tmap_f16(&T.tm_w2_lo, T.w_lo, 2, dims, strides, box2, swz2)) != AAE_OK) break;
       }
     }
     // ---- static GEMM parameters ----

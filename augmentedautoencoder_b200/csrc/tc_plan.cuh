@@ -60,12 +60,14 @@ __device__ __forceinline__ float tc_dyn_unscale(unsigned amax_bits) { return __i
 constexpr float ACT_SCALE = 16.f;     // activations (and the [0,1] input) are stored as 16 * x
 constexpr float W_SCALE = 256.f;      // weights are stored as 256 * w
 constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 512;       // launch bound: warp 0 TMA, 1 MMA, 2 TMEM allocator, 3 idle, 4.. epilogue (up to three per TMEM lane quadrant)
-// threads actually launched: 384 (two epilogue warps per quadrant) by default; AAE_TC_EPI4=1 -> 256 (one per quadrant),
-// AAE_TC_EPI12=1 -> 512 (three per quadrant) for A/B measurements
+constexpr int TC_THREADS = 512;       // warp 0 TMA, 1 MMA, 2 TMEM allocator, 3 idle, 4-15 epilogue (three per TMEM lane quadrant)
+// Threads actually launched: 512 by default.  Measured in one process (scripts/ab_inproc.py, +-0.1 %): twelve epilogue warps
+// instead of eight take conv2 / conv3 / conv4 from 1.029 / 0.886 / 0.458 to 1.000 / 0.871 / 0.452 ms (the exposed epilogue shrinks);
+// four warps: 1.170 / 0.941 / 0.468.  AAE_TC_EPI8=1 -> 384 threads, AAE_TC_EPI4=1 -> 256 (read per launch: "1" = on).
 inline int tc_block_threads() {
-  static const int n = getenv("AAE_TC_EPI4") ? 256 : (getenv("AAE_TC_EPI12") ? 512 : 384);
-  return n;
+  const char* e4 = getenv("AAE_TC_EPI4");
+  const char* e8 = getenv("AAE_TC_EPI8");
+  return (e4 && e4[0] == '1') ? 256 : ((e8 && e8[0] == '1') ? 384 : 512);
 }
 
 struct TcLayer {
@@ -185,6 +187,42 @@ __device__ __forceinline__ void tc_store_chunk(const TcGemmParams& p, const TcRo
   if (p.range_flag != nullptr && !(amax * p.out_scale < TC_F16_OVERFLOW)) atomicOr(p.range_flag, p.range_bit);
   uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
   uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+    dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+  }
+}
+
+
+// The same arithmetic as tc_store_chunk's (hi, lo) branch for the common inference case -- bias present and 16-byte aligned,
+// ReLU or identity, static scales, row-contiguous output (OUT_S2D_SPLIT / OUT_PLAIN_SPLIT) -- without the per-element mode
+// branches: the generic routine costs ~1000 issue slots per 32-column chunk, this one ~370, and the epilogue of the persistent
+// kernel is exposed (profiles/r02_conv_gemm_trace.txt).  v / x are the raw hh and cross-term accumulators.
+__device__ __forceinline__ bool tc_lean_epilogue_ok(const TcGemmParams& p) {
+  return (p.out_mode == OUT_S2D_SPLIT || p.out_mode == OUT_PLAIN_SPLIT) && p.relu != 2 && p.bias != nullptr && p.amax_bits == nullptr &&
+         (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+}
+__device__ __forceinline__ void tc_store_chunk_lean(const TcGemmParams& p, const TcRow& r, int n, const uint32_t (&v)[32], const uint32_t (&x)[32],
+                                                    float unscale, float floor_v) {
+  const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+  const float os = p.out_scale;
+  uint32_t hi[16], lo[16];
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = __ldg(bp + (j >> 2));
+    const float a0 = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(x[j])), unscale), b.x), floor_v);
+    const float a1 = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(__uint_as_float(v[j + 1]), __uint_as_float(x[j + 1])), unscale), b.y), floor_v);
+    const float a2 = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(__uint_as_float(v[j + 2]), __uint_as_float(x[j + 2])), unscale), b.z), floor_v);
+    const float a3 = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(__uint_as_float(v[j + 3]), __uint_as_float(x[j + 3])), unscale), b.w), floor_v);
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1))), fmaxf(fabsf(a2), fabsf(a3)));
+    tc::split_f16x2(a0 * os, a1 * os, hi[j >> 1], lo[j >> 1]);
+    tc::split_f16x2(a2 * os, a3 * os, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
+  }
+  if (p.range_flag != nullptr && !(amax * os < TC_F16_OVERFLOW)) atomicOr(p.range_flag, p.range_bit);
+  uint4* dh = reinterpret_cast<uint4*>(p.out_hi + r.row_off + n);
+  uint4* dl = reinterpret_cast<uint4*>(p.out_lo + r.row_off + n);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
