@@ -316,6 +316,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 
 struct TcTileSched {
   int m_pairs, n_tiles, splits;   // tiles = m_pairs * n_tiles * splits, each tile = 256 rows x 256 columns x one K range
+  int tma_out;                    // 1: tm_o_hi / tm_o_lo describe the output and each epilogue warp owns 4 KB of staging behind the ring; 2: same, plain [M, N] output
   int dbg;                        // TIMING EXPERIMENTS ONLY (AAE_TC_DEBUG, wrong results): 0 = production; 1/2 = that many products; 11 = one product AND only the hi tiles loaded
   long long* trace;               // AAE_TC_TRACE: clock64 of CTA 0 for its first 96 chunks: [g*4+0] TMA issued, +1 full barrier seen by the MMA thread, +2 MMAs issued, +3 stage seen empty again
 };
@@ -323,7 +324,8 @@ struct TcTileSched {
 template <int STAGES, int KCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const TcGemmParams p,
+                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                 const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo, const TcGemmParams p,
                  const TcTileSched sch) {
   using S = TcSmem2<STAGES, KCH>;
   constexpr int N_TILE = 256;
@@ -432,6 +434,7 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const float unscale = p.amax_bits ? p.unscale * tc_dyn_unscale(__ldg(p.amax_bits)) : p.unscale;
     const uint32_t empty_addr = leader_bar_addr(tmem_empty_bar);
     const bool lean = tc_lean_epilogue_ok(p) && !(sch.dbg == 30);
+    uint8_t* stage_out = smem + STAGES * S::STAGE_BYTES + 1024;   // behind the barriers; 4 KB per epilogue warp when sch.tma_out
     const float floor_v = p.relu == 1 ? 0.f : -INFINITY;
     int tl = 0;
     for (int t = first_tile; t < n_tiles_total; t += tile_step, ++tl) {
@@ -441,7 +444,48 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       mbar_wait(tmem_full_bar, (uint32_t)tl & 1u);
       tc_fence_after();
       if (sch.trace && blockIdx.x == 0 && threadIdx.x == 128 && tl < 16) sch.trace[392 + tl * 4 + 2] = clock64();
-      if (lean) {
+      if (lean && sch.tma_out) {
+        // TMA-store epilogue: the warp parks its 32 pixels x 32 channels (hi and lo, 64-byte rows, 64-byte swizzle) in its own
+        // 4 KB of shared memory and one lane ships both boxes with tensor stores, so the LSU sees 8 conflict-free STS.128 per
+        // thread instead of 8 STG.128 that each touch 32 different lines.  The stores drain while the next chunk is computed
+        // (and while the next tile's MMAs run); the buffer is reused once the engine has READ it.
+        uint8_t* sbuf = stage_out + (warp - 4) * 4096;
+        const int mw = m0 + q * 32;                              // the warp's first pixel: its 32 pixels lie in one image
+        const TcRow r0 = tc_decode_row(p, mw);
+        const int rsw = (lane >> 1) & 3;
+#pragma unroll 1
+        for (int c = grp; c < N_TILE / 32; c += epi_groups) {
+          uint32_t v[32], x[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
+          tmem_ld_wait();
+          const int n = n0 + c * 32;
+          if (mw >= p.M || n >= p.N) continue;
+          uint32_t hi[16], lo[16];
+          tc_lean_chunk(p, n, v, x, unscale, floor_v, hi, lo);
+          if (lane == 0) bulk_wait_read_all();                    // the previous chunk's two stores have read the buffer
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = (j ^ rsw) << 4;
+            *reinterpret_cast<uint4*>(sbuf + lane * 64 + ch) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            *reinterpret_cast<uint4*>(sbuf + 2048 + lane * 64 + ch) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+          fence_proxy_async_smem();                               // generic-proxy writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            if (sch.tma_out == 2) {
+              tma_store_2d(&tm_o_hi, sbuf, n, mw);
+              tma_store_2d(&tm_o_lo, sbuf + 2048, n, mw);
+            } else {                                              // {channel, column parity, column / 2, row parity, image * OH/2 + row / 2}
+              const int c4 = r0.b * (p.OH >> 1) + (r0.i >> 1);
+              tma_store_5d(&tm_o_hi, sbuf, n, 0, r0.j >> 1, r0.i & 1, c4);
+              tma_store_5d(&tm_o_lo, sbuf + 2048, n, 0, r0.j >> 1, r0.i & 1, c4);
+            }
+            bulk_commit_group();
+          }
+        }
+      } else if (lean) {
 #pragma unroll 1
         for (int c = grp; c < N_TILE / 32; c += epi_groups) {
           uint32_t v[32], x[32];
@@ -472,6 +516,7 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       if (lane == 0) mbar_arrive_cluster(empty_addr);
       if (sch.trace && blockIdx.x == 0 && threadIdx.x == 128 && tl < 16) sch.trace[392 + tl * 4 + 3] = clock64();
     }
+    if (lane == 0) bulk_wait_all();                               // this warp's tensor stores have landed before the CTA exits
   }
   if (sch.trace && blockIdx.x == 0 && threadIdx.x == 128) {
     unsigned long long gt;
@@ -586,7 +631,14 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
     }
     const int tiles = sch.m_pairs * sch.n_tiles * sch.splits;
     auto pk = tc_gemm2p_kernel<STAGES, KCH>;
-    AAE_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    // TMA-store epilogue: 4 KB of staging per epilogue warp behind the ring.  With six 32 KB stages that leaves room for eight
+    // epilogue warps (384 threads); the branch-free epilogue is no longer issue-bound, so eight are enough.
+    static const bool tma_out_on = getenv("AAE_TC_NO_TMA_OUT") == nullptr;
+    const bool tma_out = tma_out_on && L.tma_out && STAGES * S::STAGE_BYTES + 2048 + 8 * 4096 <= 232448;
+    const int threads = tma_out ? 384 : tc_block_threads();
+    const int smem_bytes = tma_out ? STAGES * S::STAGE_BYTES + 2048 + 8 * 4096 : S::TOTAL;
+    sch.tma_out = tma_out ? (L.gp.out_mode == OUT_PLAIN_SPLIT ? 2 : 1) : 0;
+    AAE_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem_bytes, (int)S::TOTAL)));
     static int pair_slots = 0;                       // CTA pairs that can be resident at once (asked from the driver: pairs cannot straddle GPCs)
     if (pair_slots == 0) {
       int dev = 0, sms = 0;
@@ -595,8 +647,8 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3(2u * (unsigned)std::max(1, sms / 2));
-      cfg.blockDim = dim3((unsigned)tc_block_threads());
-      cfg.dynamicSmemBytes = S::TOTAL;
+      cfg.blockDim = dim3((unsigned)threads);
+      cfg.dynamicSmemBytes = (size_t)std::max(smem_bytes, (int)S::TOTAL);
       cudaLaunchAttribute at;
       at.id = cudaLaunchAttributeClusterDimension;
       at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
@@ -606,7 +658,8 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
       pair_slots = std::min(n, std::max(1, sms / 2));
       if (getenv("AAE_TC_VERBOSE")) fprintf(stderr, "[tc] CTA pairs resident at once: %d (of %d SMs / 2 = %d)\n", n, sms, sms / 2);
     }
-    pk<<<dim3(2u * (unsigned)std::min(tiles, pair_slots)), tc_block_threads(), S::TOTAL, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w2_hi, L.tm_w2_lo, L.gp, sch);
+    pk<<<dim3(2u * (unsigned)std::min(tiles, pair_slots)), threads, smem_bytes, s>>>(L.tm_a_hi, L.tm_a_lo, L.tm_w2_hi, L.tm_w2_lo,
+                                                                                   tma_out ? L.tm_o_hi : L.tm_a_hi, tma_out ? L.tm_o_lo : L.tm_a_lo, L.gp, sch);
     AAE_LAUNCH_OK();
     if (sch.trace) {
       long long t[96 * 4 + 8 + 64];
@@ -772,6 +825,28 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
       g.out_hi = h->layers[i + 1].in_hi;
       g.out_lo = h->layers[i + 1].in_lo;
       g.out_mode = (i + 2 == h->layers.size()) ? OUT_PLAIN_SPLIT : OUT_S2D_SPLIT;
+      // the same tensor as a store target for the pair kernel's epilogue: one box = 32 consecutive pixels x 32 channels
+      TcLayer& T = h->layers[i];
+      const TcLayer& Tn = h->layers[i + 1];
+      const uint64_t Bn = ceil_div(B, Tn.BB) * Tn.BB, C = (uint64_t)g.N, OH = (uint64_t)g.OH, OW = (uint64_t)g.OW;
+      if (!T.pair || OH * OW < 32 || OW < 2 || st != AAE_OK) continue;
+      if (g.out_mode == OUT_PLAIN_SPLIT) {
+        const uint64_t dims[2] = {C, Bn * OH * OW};
+        const uint64_t strides[1] = {C * 2};
+        const uint32_t box[2] = {32, 32};
+        if ((st = make_tmap_f16(&T.tm_o_hi, g.out_hi, 2, dims, strides, box, 64)) != AAE_OK) break;
+        if ((st = make_tmap_f16(&T.tm_o_lo, g.out_lo, 2, dims, strides, box, 64)) != AAE_OK) break;
+      } else {
+        // [image, row/2, column/2, (row parity, column parity), channel] seen as {channel, column parity, column/2, row parity, image*OH/2 + row/2}
+        const uint64_t dims[5] = {C, 2, OW / 2, 2, Bn * (OH / 2)};
+        const uint64_t strides[4] = {C * 2, 4 * C * 2, 2 * C * 2, (OW / 2) * 4 * C * 2};
+        const uint32_t rows = OW >= 32 ? 1 : (uint32_t)(32 / OW);     // image rows covered by 32 consecutive pixels
+        if (rows > 1 && (rows & 1 || OH % rows != 0)) continue;
+        const uint32_t box[5] = {32, 2, (uint32_t)std::min<uint64_t>(16, OW / 2), rows > 1 ? 2u : 1u, rows > 1 ? rows / 2 : 1u};
+        if ((st = make_tmap_f16(&T.tm_o_hi, g.out_hi, 5, dims, strides, box, 64)) != AAE_OK) break;
+        if ((st = make_tmap_f16(&T.tm_o_lo, g.out_lo, 5, dims, strides, box, 64)) != AAE_OK) break;
+      }
+      T.tma_out = true;
     }
     TcLayer& D = h->layers.back();
     const int total = D.gp.taps * D.gp.chunks_per_tap;

@@ -77,6 +77,8 @@ struct TcLayer {
   __half *w_hi = nullptr, *w_lo = nullptr;      // packed weights [out_c][taps*in_c]
   CUtensorMap tm_a_hi, tm_a_lo, tm_w_hi, tm_w_lo;
   CUtensorMap tm_w2_hi, tm_w2_lo;               // weight tile halves (128 rows) for the CTA-pair kernel
+  CUtensorMap tm_o_hi, tm_o_lo;                 // output (= next layer's input) as a store target: box = 32 pixels x 32 channels
+  bool tma_out = false;                         // the persistent pair kernel may ship its epilogue through tm_o_* (TMA tensor stores)
   bool pair = false;
   TcGemmParams gp;
   int n_tile;
@@ -203,11 +205,11 @@ __device__ __forceinline__ bool tc_lean_epilogue_ok(const TcGemmParams& p) {
   return (p.out_mode == OUT_S2D_SPLIT || p.out_mode == OUT_PLAIN_SPLIT) && p.relu != 2 && p.bias != nullptr && p.amax_bits == nullptr &&
          (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
 }
-__device__ __forceinline__ void tc_store_chunk_lean(const TcGemmParams& p, const TcRow& r, int n, const uint32_t (&v)[32], const uint32_t (&x)[32],
-                                                    float unscale, float floor_v) {
+// bias + activation + range guard + (hi, lo) split of one 32-column chunk: hi[k] / lo[k] = packed fp16 pair of columns 2k, 2k+1
+__device__ __forceinline__ void tc_lean_chunk(const TcGemmParams& p, int n, const uint32_t (&v)[32], const uint32_t (&x)[32], float unscale,
+                                              float floor_v, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
   const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
   const float os = p.out_scale;
-  uint32_t hi[16], lo[16];
   float amax = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -221,6 +223,11 @@ __device__ __forceinline__ void tc_store_chunk_lean(const TcGemmParams& p, const
     tc::split_f16x2(a2 * os, a3 * os, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
   }
   if (p.range_flag != nullptr && !(amax * os < TC_F16_OVERFLOW)) atomicOr(p.range_flag, p.range_bit);
+}
+__device__ __forceinline__ void tc_store_chunk_lean(const TcGemmParams& p, const TcRow& r, int n, const uint32_t (&v)[32], const uint32_t (&x)[32],
+                                                    float unscale, float floor_v) {
+  uint32_t hi[16], lo[16];
+  tc_lean_chunk(p, n, v, x, unscale, floor_v, hi, lo);
   uint4* dh = reinterpret_cast<uint4*>(p.out_hi + r.row_off + n);
   uint4* dl = reinterpret_cast<uint4*>(p.out_lo + r.row_off + n);
 #pragma unroll
@@ -229,7 +236,6 @@ __device__ __forceinline__ void tc_store_chunk_lean(const TcGemmParams& p, const
     dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
   }
 }
-
 
 // launches the GEMM kernel instantiation that matches the layer's tile shape (CTA pair / single CTA, N tile, K chunk)
 int tc_launch_layer(const TcLayer& T, dim3 grid, cudaStream_t s);
