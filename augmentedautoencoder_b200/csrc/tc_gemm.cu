@@ -317,7 +317,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 struct TcTileSched {
   int m_pairs, n_tiles, splits;   // tiles = m_pairs * n_tiles * splits, each tile = 256 rows x 256 columns x one K range
   int tma_out;                    // 1: tm_o_hi / tm_o_lo describe the output and each epilogue warp owns 4 KB of staging behind the ring; 2: same, plain [M, N] output
-  int dbg;                        // TIMING EXPERIMENTS ONLY (AAE_TC_DEBUG, wrong results): 0 = production; 1/2 = that many products; 11 = one product AND only the hi tiles loaded
   long long* trace;               // AAE_TC_TRACE: clock64 of CTA 0 for its first 96 chunks: [g*4+0] TMA issued, +1 full barrier seen by the MMA thread, +2 MMAs issued, +3 stage seen empty again
 };
 
@@ -379,16 +378,15 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           if (sch.trace && blockIdx.x == 0 && g >= STAGES && g - STAGES < 96) sch.trace[(g - STAGES) * 4 + 3] = clock64();
           const int tap = it / p.chunks_per_tap, cc = it - tap * p.chunks_per_tap;
           uint8_t* st = smem + s * S::STAGE_BYTES;
-          const bool hi_only = sch.dbg == 11;
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], hi_only ? S::STAGE_BYTES : 2 * S::STAGE_BYTES);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);
           const uint32_t lb = leader_bar_addr(&full_bar[s]);
           const int c0 = p.tap_ch[tap] + cc * KCH;
           const int x = ow0 + p.tap_dj[tap], y = oh0 + p.tap_di[tap];
           tma_load_4d_2sm(st, &tm_a_hi, lb, c0, x, y, b0);
-          if (!hi_only) tma_load_4d_2sm(st + S::T_BYTES, &tm_a_lo, lb, c0, x, y, b0);
+          tma_load_4d_2sm(st + S::T_BYTES, &tm_a_lo, lb, c0, x, y, b0);
           const int kcol = it * KCH;
           tma_load_2d_2sm(st + 2 * S::T_BYTES, &tm_w_hi, lb, kcol, n0 + (int)rank * 128);
-          if (!hi_only) tma_load_2d_2sm(st + 3 * S::T_BYTES, &tm_w_lo, lb, kcol, n0 + (int)rank * 128);
+          tma_load_2d_2sm(st + 3 * S::T_BYTES, &tm_w_lo, lb, kcol, n0 + (int)rank * 128);
           if (sch.trace && blockIdx.x == 0 && g < 96) sch.trace[g * 4 + 0] = clock64();
         }
       }
@@ -420,8 +418,8 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           for (int k = 0; k < KCH / 16; ++k) {
             const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
             umma_f16_2sm(tmem_base, desc_advance_k(a_hi, k), desc_advance_k(w_hi, k), idesc, first);
-            if (sch.dbg == 0 || sch.dbg == 2 || sch.dbg > 20) umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, first);
-            if (sch.dbg == 0 || sch.dbg > 20) umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
+            umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_lo, k), desc_advance_k(w_hi, k), idesc, first);
+            umma_f16_2sm(tmem_base + N_TILE, desc_advance_k(a_hi, k), desc_advance_k(w_lo, k), idesc, 1u);
           }
           umma_commit_2sm(&empty_bar[s]);
           if (sch.trace && blockIdx.x == 0 && g < 96) sch.trace[g * 4 + 2] = clock64();
@@ -433,7 +431,7 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int q = warp & 3, grp = (warp - 4) >> 2, epi_groups = n_epi_warps >> 2;
     const float unscale = p.amax_bits ? p.unscale * tc_dyn_unscale(__ldg(p.amax_bits)) : p.unscale;
     const uint32_t empty_addr = leader_bar_addr(tmem_empty_bar);
-    const bool lean = tc_lean_epilogue_ok(p) && !(sch.dbg == 30);
+    const bool lean = tc_lean_epilogue_ok(p);
     uint8_t* stage_out = smem + STAGES * S::STAGE_BYTES + 1024;   // behind the barriers; 4 KB per epilogue warp when sch.tma_out
     const float floor_v = p.relu == 1 ? 0.f : -INFINITY;
     int tl = 0;
@@ -455,16 +453,22 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         const int rsw = (lane >> 1) & 3;
 #pragma unroll 1
         for (int c = grp; c < N_TILE / 32; c += epi_groups) {
+          const bool tr = sch.trace && blockIdx.x == 0 && threadIdx.x == 128 && tl == 1 && c < 24;
+          long long* tp = sch.trace + 456 + (c / epi_groups) * 8;
+          if (tr) tp[0] = clock64();
           uint32_t v[32], x[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
           tmem_ld_wait();
+          if (tr) tp[1] = clock64();
           const int n = n0 + c * 32;
           if (mw >= p.M || n >= p.N) continue;
           uint32_t hi[16], lo[16];
           tc_lean_chunk(p, n, v, x, unscale, floor_v, hi, lo);
+          if (tr) tp[2] = clock64();
           if (lane == 0) bulk_wait_read_all();                    // the previous chunk's two stores have read the buffer
           __syncwarp();
+          if (tr) tp[3] = clock64();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int ch = (j ^ rsw) << 4;
@@ -473,6 +477,7 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           }
           fence_proxy_async_smem();                               // generic-proxy writes -> visible to the TMA engine
           __syncwarp();
+          if (tr) tp[4] = clock64();
           if (lane == 0) {
             if (sch.tma_out == 2) {
               tma_store_2d(&tm_o_hi, sbuf, n, mw);
@@ -484,6 +489,7 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             }
             bulk_commit_group();
           }
+          if (tr) tp[5] = clock64();
         }
       } else if (lean) {
 #pragma unroll 1
@@ -620,23 +626,23 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
   if (persistent) {
     TcTileSched sch;
     sch.m_pairs = (int)((grid.x + 1) / 2); sch.n_tiles = (int)grid.y; sch.splits = (int)grid.z;
-    const char* dbg = getenv("AAE_TC_DEBUG");          // read per launch (scripts/ab_inproc.py)
-    sch.dbg = dbg ? atoi(dbg) : 0;
     static long long* trace_dev = nullptr;
     sch.trace = nullptr;
     if (getenv("AAE_TC_TRACE")) {
-      if (!trace_dev) { cudaMalloc(&trace_dev, (96 * 4 + 8 + 64) * sizeof(long long)); }
-      cudaMemsetAsync(trace_dev, 0, (96 * 4 + 8 + 64) * sizeof(long long), s);
+      if (!trace_dev) { cudaMalloc(&trace_dev, (96 * 4 + 8 + 64 + 64) * sizeof(long long)); }
+      cudaMemsetAsync(trace_dev, 0, (96 * 4 + 8 + 64 + 64) * sizeof(long long), s);
       sch.trace = trace_dev;
     }
     const int tiles = sch.m_pairs * sch.n_tiles * sch.splits;
     auto pk = tc_gemm2p_kernel<STAGES, KCH>;
     // TMA-store epilogue: 4 KB of staging per epilogue warp behind the ring.  With six 32 KB stages that leaves room for eight
     // epilogue warps (384 threads); the branch-free epilogue is no longer issue-bound, so eight are enough.
-    static const bool tma_out_on = getenv("AAE_TC_NO_TMA_OUT") == nullptr;
-    const bool tma_out = tma_out_on && L.tma_out && STAGES * S::STAGE_BYTES + 2048 + 8 * 4096 <= 232448;
-    const int threads = tma_out ? 384 : tc_block_threads();
-    const int smem_bytes = tma_out ? STAGES * S::STAGE_BYTES + 2048 + 8 * 4096 : S::TOTAL;
+    const char* no_tma = getenv("AAE_TC_NO_TMA_OUT");            // read per launch (scripts/ab_inproc.py)
+    const bool tma_out_on = !(no_tma && no_tma[0] == '1');
+    constexpr int EPI_TMA = STAGES * S::STAGE_BYTES + 2048 + 12 * 4096 <= 232448 ? 12 : 8;   // epilogue warps the staging has room for
+    const bool tma_out = tma_out_on && L.tma_out && STAGES * S::STAGE_BYTES + 2048 + EPI_TMA * 4096 <= 232448;
+    const int threads = tma_out ? 128 + 32 * EPI_TMA : tc_block_threads();
+    const int smem_bytes = tma_out ? STAGES * S::STAGE_BYTES + 2048 + EPI_TMA * 4096 : S::TOTAL;
     sch.tma_out = tma_out ? (L.gp.out_mode == OUT_PLAIN_SPLIT ? 2 : 1) : 0;
     AAE_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem_bytes, (int)S::TOTAL)));
     static int pair_slots = 0;                       // CTA pairs that can be resident at once (asked from the driver: pairs cannot straddle GPCs)
@@ -662,12 +668,16 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
                                                                                    tma_out ? L.tm_o_hi : L.tm_a_hi, tma_out ? L.tm_o_lo : L.tm_a_lo, L.gp, sch);
     AAE_LAUNCH_OK();
     if (sch.trace) {
-      long long t[96 * 4 + 8 + 64];
+      long long t[96 * 4 + 8 + 64 + 64];
       cudaStreamSynchronize(s);
       cudaMemcpy(t, sch.trace, sizeof(t), cudaMemcpyDeviceToHost);
       fprintf(stderr, "[gemm2p trace] N=%d taps=%d chunks/tap=%d: chunk: issue | +full seen | +mma issued | next-use empty seen (clocks, relative to chunk 0 issue)\n", L.gp.N, L.gp.taps, L.gp.chunks_per_tap);
       fprintf(stderr, "  CTA 0 (epilogue warp 4): %lld cycles in %lld ns -> SM clock %.0f MHz during this kernel\n", t[386] - t[384], t[387] - t[385],
               1e3 * (double)(t[386] - t[384]) / (double)(t[387] - t[385]));
+      for (int k = 0; k < 4; ++k)
+        fprintf(stderr, "  tile 1, warp 4, chunk round %d: tcgen05.ld %lld | math %lld | wait for buffer %lld | STS + proxy fence %lld | TMA issue %lld | (next round starts +%lld)\n", k,
+                t[456 + k * 8 + 1] - t[456 + k * 8], t[456 + k * 8 + 2] - t[456 + k * 8 + 1], t[456 + k * 8 + 3] - t[456 + k * 8 + 2],
+                t[456 + k * 8 + 4] - t[456 + k * 8 + 3], t[456 + k * 8 + 5] - t[456 + k * 8 + 4], k < 3 ? t[456 + (k + 1) * 8] - t[456 + k * 8 + 5] : 0LL);
       for (int tl = 0; tl < 15; ++tl)
         fprintf(stderr, "  tile %2d: epilogue warp 4 sees accumulators at %8lld, done +%6lld | issuer waits for drained TMEM from %8lld for %6lld\n", tl,
                 t[392 + tl * 4 + 2] - t[384], t[392 + tl * 4 + 3] - t[392 + tl * 4 + 2], t[392 + tl * 4 + 0] - t[384], t[392 + tl * 4 + 1] - t[392 + tl * 4 + 0]);
@@ -707,7 +717,10 @@ int tc_dev_alloc(void** p, size_t bytes) {
 }
 
 int tc_launch_layer(const TcLayer& T, dim3 grid, cudaStream_t s) {
-  if (T.pair && T.kch == 32) return launch_tc_gemm2<6, 32>(T, grid, s);
+  if (T.pair && T.kch == 32) {
+    const char* s5 = getenv("AAE_TC_S5");                         // five stages leave room for twelve epilogue warps' staging
+    return (s5 && s5[0] == '1') ? launch_tc_gemm2<5, 32>(T, grid, s) : launch_tc_gemm2<6, 32>(T, grid, s);
+  }
   if (T.pair) return launch_tc_gemm2<3, 64>(T, grid, s);
   if (T.n_tile == 256 && T.kch == 32) return launch_tc_gemm<256, 4, 32>(T, grid, s);
   if (T.n_tile == 256) return launch_tc_gemm<256, TC_STAGES, 64>(T, grid, s);
@@ -768,12 +781,8 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
       const uint64_t C4 = 4ull * T.in_c, W2 = T.in_w / 2, H2 = T.in_h / 2;
       const uint64_t dims[4] = {C4, W2, H2, (uint64_t)B_pad};
       const uint64_t strides[3] = {C4 * 2, W2 * C4 * 2, H2 * W2 * C4 * 2};
-      uint32_t box[4] = {(uint32_t)T.kch, (uint32_t)T.BW, (uint32_t)T.BH, (uint32_t)T.BB};
-      int swz = 2 * T.kch;
-      // HYPOTHESIS TEST ONLY (AAE_TC_DEBUG_BOX128=1, wrong results): the same bytes per stage fetched as 128-byte rows (64 channels x half
-      // the pixels) instead of 64-byte rows -- is the L2 -> SM path limited by requests rather than bytes?
-      const bool dbg128 = getenv("AAE_TC_DEBUG_BOX128") != nullptr && T.kch == 32;
-      if (dbg128) { box[0] = 64; if (T.BH >= 2) box[2] = T.BH / 2; else box[1] = T.BW / 2; swz = 128; }
+      const uint32_t box[4] = {(uint32_t)T.kch, (uint32_t)T.BW, (uint32_t)T.BH, (uint32_t)T.BB};
+      const int swz = 2 * T.kch;
       if ((st = make_tmap_f16(&T.tm_a_hi, T.in_hi, 4, dims, strides, box, swz)) != AAE_OK) break;
       if ((st = make_tmap_f16(&T.tm_a_lo, T.in_lo, 4, dims, strides, box, swz)) != AAE_OK) break;
     } else {
@@ -792,9 +801,8 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
       if ((st = make_tmap_f16(&T.tm_w_lo, T.w_lo, 2, dims, strides, box, 2 * T.kch)) != AAE_OK) break;
       T.pair = !dense && T.n_tile == 256 && T.out_c % 256 == 0 && getenv("AAE_TC_1CTA") == nullptr;
       if (T.pair) {
-        uint32_t box2[2] = {(uint32_t)T.kch, 128};
-        int swz2 = 2 * T.kch;
-        if (getenv("AAE_TC_DEBUG_BOX128") != nullptr && T.kch == 32) { box2[0] = 64; box2[1] = 64; swz2 = 128; }   // see above
+        const uint32_t box2[2] = {(uint32_t)T.kch, 128};
+        const int swz2 = 2 * T.kch;
         if ((st = make_tmap_f16(&T.tm_w2_hi, T.w_hi, 2, dims, strides, box2, swz2)) != AAE_OK) break;
         if ((st = make_tmap_f16(&T.tm_w2_lo, T.w_lo, 2, dims, strides, box2, swz2)) != AAE_OK) break;
       }

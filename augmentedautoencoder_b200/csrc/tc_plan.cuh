@@ -156,12 +156,23 @@ __device__ __forceinline__ void tc_store_chunk(const TcGemmParams& p, const TcRo
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
     return;
   }
+  // bias + activation with the mode tests hoisted out of the element loops (per-element tests made this routine ~1000 issue
+  // slots per chunk, and the epilogue of a one-CTA-per-SM GEMM is exposed)
+  float b[32];
+  if (p.bias != nullptr) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float a = f[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-    if (p.relu == 1) a = fmaxf(a, 0.f);
-    else if (p.relu == 2) a = 1.f / (1.f + expf(-a));
-    f[j] = a;
+    for (int j = 0; j < 32; ++j) b[j] = __ldg(p.bias + n + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = 0.f;
+  }
+  if (p.relu == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = 1.f / (1.f + expf(-(f[j] + b[j])));
+  } else {
+    const float floor_v = p.relu == 1 ? 0.f : -INFINITY;       // fmaxf(a, -inf) = a
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j] + b[j], floor_v);
   }
   if (p.out_mode == OUT_D2S_F32) {
     const int cr = p.cout_real;

@@ -1,7 +1,7 @@
 """In-process A/B of a per-launch environment switch (process-to-process noise on the pool's boxes is +-5 %, more than most kernel
 changes): alternates the variable between two values batch by batch and compares the encoder's stage times.
-    python scripts/ab_inproc.py AAE_TC_MMA_ORDER 0 1 [--batches 60]
-Only switches that the library reads on every launch work here (AAE_TC_MMA_ORDER)."""
+    python scripts/ab_inproc.py AAE_TC_NO_TMA_OUT 0 1 [--batches 60]
+Only switches that the library reads on every launch work here (AAE_TC_NO_TMA_OUT, AAE_TC_S5, AAE_TC_EPI8 / AAE_TC_EPI4)."""
 import ctypes as C
 import os
 import statistics
