@@ -316,7 +316,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 
 struct TcTileSched {
   int m_pairs, n_tiles, splits;   // tiles = m_pairs * n_tiles * splits, each tile = 256 rows x 256 columns x one K range
-  int tma_out;                    // 1: tm_o_hi / tm_o_lo describe the output and each epilogue warp owns 4 KB of staging behind the ring; 2: same, plain [M, N] output
+  int tma_out;                    // > 0: tm_o_hi / tm_o_lo describe the output and each epilogue warp owns 4 KB of staging behind the ring:
+                                  // 1 space-to-depth (hi, lo), 2 plain (hi, lo), 3 depth-to-space (hi, lo), 4 fp32 [M, N] (tm_o_hi only)
   long long* trace;               // AAE_TC_TRACE: clock64 of CTA 0 for its first 96 chunks: [g*4+0] TMA issued, +1 full barrier seen by the MMA thread, +2 MMAs issued, +3 stage seen empty again
 };
 
@@ -442,54 +443,63 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       mbar_wait(tmem_full_bar, (uint32_t)tl & 1u);
       tc_fence_after();
       if (sch.trace && blockIdx.x == 0 && threadIdx.x == 128 && tl < 16) sch.trace[392 + tl * 4 + 2] = clock64();
-      if (lean && sch.tma_out) {
-        // TMA-store epilogue: the warp parks its 32 pixels x 32 channels (hi and lo, 64-byte rows, 64-byte swizzle) in its own
-        // 4 KB of shared memory and one lane ships both boxes with tensor stores, so the LSU sees 8 conflict-free STS.128 per
-        // thread instead of 8 STG.128 that each touch 32 different lines.  The stores drain while the next chunk is computed
-        // (and while the next tile's MMAs run); the buffer is reused once the engine has READ it.
+      if ((lean && sch.tma_out >= 1 && sch.tma_out <= 3) || sch.tma_out == 4) {
+        // TMA-store epilogue: the warp parks its 32 pixels x 32 columns (hi and lo with 64-byte rows and 64-byte swizzle, or fp32
+        // with 128-byte rows and 128-byte swizzle) in its own 4 KB of shared memory and one lane ships the box(es) with tensor
+        // stores, so the LSU sees 8 conflict-free STS.128 per thread instead of 8 STG.128 that each touch 32 different lines.
+        // The stores drain while the next chunk is computed (and while the next tile's MMAs run); the buffer is reused once the
+        // engine has READ it.
         uint8_t* sbuf = stage_out + (warp - 4) * 4096;
         const int mw = m0 + q * 32;                              // the warp's first pixel: its 32 pixels lie in one image
         const TcRow r0 = tc_decode_row(p, mw);
         const int rsw = (lane >> 1) & 3;
 #pragma unroll 1
         for (int c = grp; c < N_TILE / 32; c += epi_groups) {
-          const bool tr = sch.trace && blockIdx.x == 0 && threadIdx.x == 128 && tl == 1 && c < 24;
-          long long* tp = sch.trace + 456 + (c / epi_groups) * 8;
-          if (tr) tp[0] = clock64();
           uint32_t v[32], x[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
           tmem_ld_wait();
-          if (tr) tp[1] = clock64();
           const int n = n0 + c * 32;
           if (mw >= p.M || n >= p.N) continue;
-          uint32_t hi[16], lo[16];
-          tc_lean_chunk(p, n, v, x, unscale, floor_v, hi, lo);
-          if (tr) tp[2] = clock64();
-          if (lane == 0) bulk_wait_read_all();                    // the previous chunk's two stores have read the buffer
-          __syncwarp();
-          if (tr) tp[3] = clock64();
+          if (sch.tma_out == 4) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ch = (j ^ rsw) << 4;
-            *reinterpret_cast<uint4*>(sbuf + lane * 64 + ch) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            *reinterpret_cast<uint4*>(sbuf + 2048 + lane * 64 + ch) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint((__uint_as_float(v[j]) + __uint_as_float(x[j])) * unscale);
+            if (lane == 0) bulk_wait_read_all();                  // the previous chunk's store has read the buffer
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint32_t hi[16], lo[16];
+            tc_lean_chunk(p, n, v, x, unscale, floor_v, hi, lo);
+            if (lane == 0) bulk_wait_read_all();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ch = (j ^ rsw) << 4;
+              *reinterpret_cast<uint4*>(sbuf + lane * 64 + ch) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              *reinterpret_cast<uint4*>(sbuf + 2048 + lane * 64 + ch) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
           }
           fence_proxy_async_smem();                               // generic-proxy writes -> visible to the TMA engine
           __syncwarp();
-          if (tr) tp[4] = clock64();
           if (lane == 0) {
-            if (sch.tma_out == 2) {
+            if (sch.tma_out == 4) {
+              tma_store_2d(&tm_o_hi, sbuf, 2 * n, mw);            // fp32 column n = fp16 column 2n of the map
+            } else if (sch.tma_out == 2) {
               tma_store_2d(&tm_o_hi, sbuf, n, mw);
               tma_store_2d(&tm_o_lo, sbuf + 2048, n, mw);
-            } else {                                              // {channel, column parity, column / 2, row parity, image * OH/2 + row / 2}
+            } else if (sch.tma_out == 1) {                        // {channel, column parity, column / 2, row parity, image * OH/2 + row / 2}
               const int c4 = r0.b * (p.OH >> 1) + (r0.i >> 1);
               tma_store_5d(&tm_o_hi, sbuf, n, 0, r0.j >> 1, r0.i & 1, c4);
               tma_store_5d(&tm_o_lo, sbuf + 2048, n, 0, r0.j >> 1, r0.i & 1, c4);
+            } else {                                              // depth-to-space: {channel, x parity, column, y parity, image * OH + row}
+              const int cq = p.N >> 2, cls = n / cq, co = n - cls * cq;
+              tma_store_5d(&tm_o_hi, sbuf, co, cls & 1, r0.j, cls >> 1, r0.b * p.OH + r0.i);
+              tma_store_5d(&tm_o_lo, sbuf + 2048, co, cls & 1, r0.j, cls >> 1, r0.b * p.OH + r0.i);
             }
             bulk_commit_group();
           }
-          if (tr) tp[5] = clock64();
         }
       } else if (lean) {
 #pragma unroll 1
@@ -640,10 +650,11 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
     const char* no_tma = getenv("AAE_TC_NO_TMA_OUT");            // read per launch (scripts/ab_inproc.py)
     const bool tma_out_on = !(no_tma && no_tma[0] == '1');
     constexpr int EPI_TMA = STAGES * S::STAGE_BYTES + 2048 + 12 * 4096 <= 232448 ? 12 : 8;   // epilogue warps the staging has room for
-    const bool tma_out = tma_out_on && L.tma_out && STAGES * S::STAGE_BYTES + 2048 + EPI_TMA * 4096 <= 232448;
+    const bool f32_target_ok = L.gp.out_mode != OUT_F32 || (sch.splits == 1 && L.gp.out_f32 == L.tma_f32_base);
+    const bool tma_out = tma_out_on && L.tma_out && f32_target_ok && STAGES * S::STAGE_BYTES + 2048 + EPI_TMA * 4096 <= 232448;
     const int threads = tma_out ? 128 + 32 * EPI_TMA : tc_block_threads();
     const int smem_bytes = tma_out ? STAGES * S::STAGE_BYTES + 2048 + EPI_TMA * 4096 : S::TOTAL;
-    sch.tma_out = tma_out ? (L.gp.out_mode == OUT_PLAIN_SPLIT ? 2 : 1) : 0;
+    sch.tma_out = !tma_out ? 0 : L.gp.out_mode == OUT_S2D_SPLIT ? 1 : L.gp.out_mode == OUT_PLAIN_SPLIT ? 2 : L.gp.out_mode == OUT_D2S_SPLIT ? 3 : 4;
     AAE_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem_bytes, (int)S::TOTAL)));
     static int pair_slots = 0;                       // CTA pairs that can be resident at once (asked from the driver: pairs cannot straddle GPCs)
     if (pair_slots == 0) {
@@ -729,6 +740,51 @@ int tc_launch_layer(const TcLayer& T, dim3 grid, cudaStream_t s) {
   if (T.n_tile == 32 && T.kch == 32) return launch_tc_gemm<32, 6, 32>(T, grid, s);
   set_error("tc_launch_layer: no kernel for n_tile=%d kch=%d", T.n_tile, T.kch);
   return AAE_ERR_UNSUPPORTED;
+}
+
+int tc_layer_setup_out_maps(TcLayer& T, long long out_rows_pad) {
+  const TcGemmParams& g = T.gp;
+  const uint64_t OH = (uint64_t)g.OH, OW = (uint64_t)g.OW, R = (uint64_t)out_rows_pad;
+  T.tma_out = false;
+  if (OH * OW < 32 && g.out_mode != OUT_F32) return AAE_OK;
+  const uint32_t rows = OW >= 32 ? 1u : (uint32_t)(32 / std::max<uint64_t>(OW, 1));   // image rows covered by 32 consecutive pixels
+  if (g.out_mode == OUT_F32) {                       // fp32 [rows, N] seen as fp16 [rows, 2N]: box = 32 rows x 32 floats (128-byte rows)
+    const uint64_t dims[2] = {2ull * g.N, R};
+    const uint64_t strides[1] = {4ull * g.N};
+    const uint32_t box[2] = {64, 32};
+    AAE_TRY(make_tmap_f16(&T.tm_o_hi, g.out_f32, 2, dims, strides, box, 128));
+    T.tm_o_lo = T.tm_o_hi;
+    T.tma_f32_base = g.out_f32;
+  } else if (g.out_mode == OUT_PLAIN_SPLIT) {
+    const uint64_t C = (uint64_t)g.N;
+    const uint64_t dims[2] = {C, R * OH * OW};
+    const uint64_t strides[1] = {C * 2};
+    const uint32_t box[2] = {32, 32};
+    AAE_TRY(make_tmap_f16(&T.tm_o_hi, g.out_hi, 2, dims, strides, box, 64));
+    AAE_TRY(make_tmap_f16(&T.tm_o_lo, g.out_lo, 2, dims, strides, box, 64));
+  } else if (g.out_mode == OUT_S2D_SPLIT) {
+    // [image, row/2, column/2, (row parity, column parity), channel] seen as {channel, column parity, column/2, row parity, image*OH/2 + row/2}
+    const uint64_t C = (uint64_t)g.N;
+    if (OW < 2 || (rows > 1 && ((rows & 1) || OH % rows != 0))) return AAE_OK;
+    const uint64_t dims[5] = {C, 2, OW / 2, 2, R * (OH / 2)};
+    const uint64_t strides[4] = {C * 2, 4 * C * 2, 2 * C * 2, (OW / 2) * 4 * C * 2};
+    const uint32_t box[5] = {32, 2, (uint32_t)std::min<uint64_t>(16, OW / 2), rows > 1 ? 2u : 1u, rows > 1 ? rows / 2 : 1u};
+    AAE_TRY(make_tmap_f16(&T.tm_o_hi, g.out_hi, 5, dims, strides, box, 64));
+    AAE_TRY(make_tmap_f16(&T.tm_o_lo, g.out_lo, 5, dims, strides, box, 64));
+  } else if (g.out_mode == OUT_D2S_SPLIT) {
+    // [image, 2 row + y parity, 2 column + x parity, channel] seen as {channel, x parity, column, y parity, image*OH + row}
+    const uint64_t cq = (uint64_t)g.N / 4;
+    if (cq < 32 || cq % 32 != 0 || OH % rows != 0) return AAE_OK;
+    const uint64_t dims[5] = {cq, 2, OW, 2, R * OH};
+    const uint64_t strides[4] = {cq * 2, 2 * cq * 2, 2 * OW * cq * 2, 4 * OW * cq * 2};
+    const uint32_t box[5] = {32, 1, (uint32_t)std::min<uint64_t>(32, OW), 1, rows};
+    AAE_TRY(make_tmap_f16(&T.tm_o_hi, g.out_hi, 5, dims, strides, box, 64));
+    AAE_TRY(make_tmap_f16(&T.tm_o_lo, g.out_lo, 5, dims, strides, box, 64));
+  } else {
+    return AAE_OK;
+  }
+  T.tma_out = true;
+  return AAE_OK;
 }
 
 int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
@@ -833,28 +889,7 @@ int tc_encoder_create(int device, const aae_net_cfg* cfg, TcEncoder** out) {
       g.out_hi = h->layers[i + 1].in_hi;
       g.out_lo = h->layers[i + 1].in_lo;
       g.out_mode = (i + 2 == h->layers.size()) ? OUT_PLAIN_SPLIT : OUT_S2D_SPLIT;
-      // the same tensor as a store target for the pair kernel's epilogue: one box = 32 consecutive pixels x 32 channels
-      TcLayer& T = h->layers[i];
-      const TcLayer& Tn = h->layers[i + 1];
-      const uint64_t Bn = ceil_div(B, Tn.BB) * Tn.BB, C = (uint64_t)g.N, OH = (uint64_t)g.OH, OW = (uint64_t)g.OW;
-      if (!T.pair || OH * OW < 32 || OW < 2 || st != AAE_OK) continue;
-      if (g.out_mode == OUT_PLAIN_SPLIT) {
-        const uint64_t dims[2] = {C, Bn * OH * OW};
-        const uint64_t strides[1] = {C * 2};
-        const uint32_t box[2] = {32, 32};
-        if ((st = make_tmap_f16(&T.tm_o_hi, g.out_hi, 2, dims, strides, box, 64)) != AAE_OK) break;
-        if ((st = make_tmap_f16(&T.tm_o_lo, g.out_lo, 2, dims, strides, box, 64)) != AAE_OK) break;
-      } else {
-        // [image, row/2, column/2, (row parity, column parity), channel] seen as {channel, column parity, column/2, row parity, image*OH/2 + row/2}
-        const uint64_t dims[5] = {C, 2, OW / 2, 2, Bn * (OH / 2)};
-        const uint64_t strides[4] = {C * 2, 4 * C * 2, 2 * C * 2, (OW / 2) * 4 * C * 2};
-        const uint32_t rows = OW >= 32 ? 1 : (uint32_t)(32 / OW);     // image rows covered by 32 consecutive pixels
-        if (rows > 1 && (rows & 1 || OH % rows != 0)) continue;
-        const uint32_t box[5] = {32, 2, (uint32_t)std::min<uint64_t>(16, OW / 2), rows > 1 ? 2u : 1u, rows > 1 ? rows / 2 : 1u};
-        if ((st = make_tmap_f16(&T.tm_o_hi, g.out_hi, 5, dims, strides, box, 64)) != AAE_OK) break;
-        if ((st = make_tmap_f16(&T.tm_o_lo, g.out_lo, 5, dims, strides, box, 64)) != AAE_OK) break;
-      }
-      T.tma_out = true;
+      if (h->layers[i].pair && (st = tc_layer_setup_out_maps(h->layers[i], (long long)ceil_div(B, h->layers[i + 1].BB) * h->layers[i + 1].BB)) != AAE_OK) break;
     }
     TcLayer& D = h->layers.back();
     const int total = D.gp.taps * D.gp.chunks_per_tap;
@@ -1195,6 +1230,9 @@ int tc_decoder_create(int device, const aae_net_cfg* cfg, TcDecoder** out) {
       h->layers[i].gp.out_lo = h->layers[i + 1].in_lo;
       h->layers[i].gp.range_flag = h->range_flag;       // bit i: the activation written by layer i (0 = dense_1)
       h->layers[i].gp.range_bit = 1u << i;
+      if (h->layers[i].pair && h->layers[i].gp.out_mode == OUT_D2S_SPLIT &&
+          (st = tc_layer_setup_out_maps(h->layers[i], (long long)ceil_div(B, h->layers[i + 1].BB) * h->layers[i + 1].BB)) != AAE_OK)
+        break;
     }
   }
   if (st != AAE_OK) { tc_decoder_destroy(h); return st; }

@@ -79,6 +79,7 @@ struct TcLayer {
   CUtensorMap tm_w2_hi, tm_w2_lo;               // weight tile halves (128 rows) for the CTA-pair kernel
   CUtensorMap tm_o_hi, tm_o_lo;                 // output (= next layer's input) as a store target: box = 32 pixels x 32 channels
   bool tma_out = false;                         // the persistent pair kernel may ship its epilogue through tm_o_* (TMA tensor stores)
+  const float* tma_f32_base = nullptr;          // OUT_F32: tm_o_hi describes THIS buffer (fp32 [rows, N] seen as fp16 [rows, 2N]); other targets use plain stores
   bool pair = false;
   TcGemmParams gp;
   int n_tile;
@@ -208,23 +209,23 @@ __device__ __forceinline__ void tc_store_chunk(const TcGemmParams& p, const TcRo
 }
 
 
-// The same arithmetic as tc_store_chunk's (hi, lo) branch for the common inference case -- bias present and 16-byte aligned,
-// ReLU or identity, static scales, row-contiguous output (OUT_S2D_SPLIT / OUT_PLAIN_SPLIT) -- without the per-element mode
-// branches: the generic routine costs ~1000 issue slots per 32-column chunk, this one ~370, and the epilogue of the persistent
-// kernel is exposed (profiles/r02_conv_gemm_trace.txt).  v / x are the raw hh and cross-term accumulators.
+// The same arithmetic as tc_store_chunk's (hi, lo) branch without its per-element mode tests, for the persistent kernel whose
+// epilogue is exposed (profiles/r02_conv_gemm_trace.txt): ReLU or identity, bias absent or 16-byte aligned, any of the three
+// (hi, lo) layouts.  v / x are the raw hh and cross-term accumulators.
 __device__ __forceinline__ bool tc_lean_epilogue_ok(const TcGemmParams& p) {
-  return (p.out_mode == OUT_S2D_SPLIT || p.out_mode == OUT_PLAIN_SPLIT) && p.relu != 2 && p.bias != nullptr && p.amax_bits == nullptr &&
+  return (p.out_mode == OUT_S2D_SPLIT || p.out_mode == OUT_PLAIN_SPLIT || p.out_mode == OUT_D2S_SPLIT) && p.relu != 2 &&
          (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
 }
 // bias + activation + range guard + (hi, lo) split of one 32-column chunk: hi[k] / lo[k] = packed fp16 pair of columns 2k, 2k+1
-__device__ __forceinline__ void tc_lean_chunk(const TcGemmParams& p, int n, const uint32_t (&v)[32], const uint32_t (&x)[32], float unscale,
-                                              float floor_v, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+template <bool BIAS>
+__device__ __forceinline__ void tc_lean_chunk_t(const TcGemmParams& p, int n, const uint32_t (&v)[32], const uint32_t (&x)[32], float unscale,
+                                                float floor_v, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
   const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
   const float os = p.out_scale;
   float amax = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const float4 b = __ldg(bp + (j >> 2));
+    const float4 b = BIAS ? __ldg(bp + (j >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float a0 = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(x[j])), unscale), b.x), floor_v);
     const float a1 = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(__uint_as_float(v[j + 1]), __uint_as_float(x[j + 1])), unscale), b.y), floor_v);
     const float a2 = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(__uint_as_float(v[j + 2]), __uint_as_float(x[j + 2])), unscale), b.z), floor_v);
@@ -235,12 +236,22 @@ __device__ __forceinline__ void tc_lean_chunk(const TcGemmParams& p, int n, cons
   }
   if (p.range_flag != nullptr && !(amax * os < TC_F16_OVERFLOW)) atomicOr(p.range_flag, p.range_bit);
 }
+__device__ __forceinline__ void tc_lean_chunk(const TcGemmParams& p, int n, const uint32_t (&v)[32], const uint32_t (&x)[32], float unscale,
+                                              float floor_v, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+  if (p.bias != nullptr) tc_lean_chunk_t<true>(p, n, v, x, unscale, floor_v, hi, lo);
+  else tc_lean_chunk_t<false>(p, n, v, x, unscale, floor_v, hi, lo);
+}
 __device__ __forceinline__ void tc_store_chunk_lean(const TcGemmParams& p, const TcRow& r, int n, const uint32_t (&v)[32], const uint32_t (&x)[32],
                                                     float unscale, float floor_v) {
   uint32_t hi[16], lo[16];
   tc_lean_chunk(p, n, v, x, unscale, floor_v, hi, lo);
-  uint4* dh = reinterpret_cast<uint4*>(p.out_hi + r.row_off + n);
-  uint4* dl = reinterpret_cast<uint4*>(p.out_lo + r.row_off + n);
+  long long off = r.row_off + n;
+  if (p.out_mode == OUT_D2S_SPLIT) {
+    const int cq = p.N >> 2, cls = n / cq, co = n - cls * cq;     // a 32-column chunk never straddles a parity class (cq % 32 == 0)
+    off = ((long long)(r.b * 2 * p.OH + 2 * r.i + (cls >> 1)) * (2 * p.OW) + 2 * r.j + (cls & 1)) * cq + co;
+  }
+  uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
+  uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
@@ -255,5 +266,9 @@ int tc_dev_alloc(void** p, size_t bytes);
 // (taps = unit-stride boxes): fills tm_a_*, allocates w_hi/w_lo [ceil(N / n_tile) * n_tile][taps * in_c] and their maps.
 // T.{in_h,in_w,in_c,taps,BW,BH,BB,n_tile,kch,gp.N} must be set; with alloc_input = false T.in_hi/in_lo are the caller's.
 int tc_layer_setup_plain(TcLayer& T, int B, bool pair_ok, bool alloc_input);
+// Store-side tensor maps for the persistent pair kernel's epilogue (T.tma_out): the (hi, lo) output of a layer whose gp.out_mode
+// is OUT_S2D_SPLIT / OUT_PLAIN_SPLIT / OUT_D2S_SPLIT (out_rows_pad = images the destination buffers hold), or an fp32 [rows, N]
+// buffer for OUT_F32 (out_rows_pad = rows it holds).  Leaves T.tma_out false when the geometry has no 32-pixel box.
+int tc_layer_setup_out_maps(TcLayer& T, long long out_rows_pad);
 
 }  // namespace aae

@@ -824,6 +824,13 @@ int tc_train_create(TcEncoder* enc, TcDecoder* dec, int max_batch, TcTrainPlan**
   if (st == AAE_OK) st = tc_dev_alloc((void**)&h->partials, part_max * sizeof(float));
   if (st == AAE_OK) st = tc_dev_alloc((void**)&h->wm, wm_max * sizeof(float));
   h->raw_floats = raw_max; h->partial_floats = part_max; h->wm_floats = wm_max;
+  // the persistent pair kernel ships unsplit dgrad results to `raw` with tensor stores
+  for (size_t u = 0; u < h->units.size() && st == AAE_OK; ++u) {
+    TcLayer& T = h->units[u].dg;
+    if (!T.pair) continue;
+    T.gp.out_f32 = h->raw;
+    st = tc_layer_setup_out_maps(T, (long long)(raw_max / (size_t)T.gp.N));
+  }
   if (st != AAE_OK) { tc_train_destroy(h); return st; }
   *out = h;
   return AAE_OK;
