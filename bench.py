@@ -51,9 +51,9 @@ ENC_FLOP_PER_CROP = 2 * 2140667904
 LAYER_MAC_PER_CROP = [39321600, 838860800, 838860800, 419430400, 4194304]
 MATCH_BYTES = N_ROWS * LATENT * 4 + BATCH * LATENT * 4 + BATCH * 8
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures of this exact workload
-# (profiles/r02_ncu_*.txt; precision=tc, batch 256).  Algorithmic bytes beside them: conv1 = 12.6 MB crops + 537 MB (hi,lo)
+# (profiles/r02_ncu_*.txt, conv2 / conv3 from the re-capture r02b_ncu_*.txt; precision=tc, batch 256).  Algorithmic bytes beside them: conv1 = 12.6 MB crops + 537 MB (hi,lo)
 # output; conv2 = 537 MB (hi,lo) input + 3.3 MB weights + 268 MB output = 808 MB; match = 47.36 MB.
-NCU_TRAFFIC = {"tc": {"conv1": 12700160 + 482454784, "conv2": 555446272 + 235288064, "match": 47427584 + 0}}
+NCU_TRAFFIC = {"tc": {"conv1": 12700160 + 482454784, "conv2": 559772160 + 239571968, "conv3": 619160064 + 117579264, "match": 47427584 + 0}}
 METRIC = "pose queries/sec (encode+codebook NN)"
 
 
