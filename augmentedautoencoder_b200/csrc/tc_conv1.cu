@@ -45,6 +45,7 @@ struct Conv1Params {
   __half* out_hi;
   __half* out_lo;
   unsigned* range_flag;    // run-time range guard (tc_plan.cuh): bit 0 = this layer's activation overflowed fp16 at out_scale
+  long long* trace;        // AAE_C1_TRACE: clock64 stamps of CTA 0 (first 12 tiles): [i*8 + 0..2] builder start / stage free / tile built, +3,4 MMA issuer got accumulator / operands, +5,6 epilogue warp 4 start / end
 };
 
 template <int N>
@@ -341,7 +342,13 @@ __device__ __forceinline__ void bytes_to_half4(uint32_t x, uint32_t& lo2, uint32
   hi2 = *reinterpret_cast<const uint32_t*>(&hb);
 }
 
-__global__ void __launch_bounds__(C1_THREADS, 1)
+// Epilogue warps of the uint8 kernel: 16 (four per TMEM lane quadrant, one 32-channel chunk of the tile each) or 8 (two chunks each).
+// In-kernel trace (profiles/r02_conv1_trace.txt): the epilogue paces the kernel -- one chunk costs a warp ~1.7 k cycles of mostly
+// latency (TMEM load, split, proxy fence, tensor-store issue), the builders and the MMAs are far ahead.
+constexpr int U8_MAX_EPI_WARPS = 16;
+constexpr int U8_MAX_THREADS = 32 * (4 + U8_MAX_EPI_WARPS + 1);
+
+__global__ void __launch_bounds__(U8_MAX_THREADS, 1)
 tc_conv1_u8_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                    const __grid_constant__ CUtensorMap tm_out_hi, const __grid_constant__ CUtensorMap tm_out_lo, const Conv1Params p) {
   constexpr int N = 128, CIN = 3;
@@ -360,17 +367,18 @@ tc_conv1_u8_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
   __shared__ float bias_s[N];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_epi = ((int)blockDim.x >> 5) - 5, mma_warp = 4 + n_epi;      // 8 or 16 epilogue warps, then the issuer warp
   constexpr int TMEM_COLS = 2 * N;
   if (threadIdx.x < N) bias_s[threadIdx.x] = p.bias[threadIdx.x] * p.out_scale;     // relu(x) * s == relu(x * s) for s > 0
   for (int i = threadIdx.x; i < 2 * U8_PIX_BUF / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(pix)[i] = 0u;   // lead-in / tail stay zero
-  if (warp == C1_MMA_WARP && lane == 0) {
+  if (warp == mma_warp && lane == 0) {
     prefetch_tmap(&tm_w_hi); prefetch_tmap(&tm_w_lo); prefetch_tmap(&tm_out_hi); prefetch_tmap(&tm_out_lo);
     mbar_init(w_full, 1);
     for (int s = 0; s < U8_A_STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], C1_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], n_epi); }
     fence_barrier_init();
   }
-  if (warp == C1_MMA_WARP) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  if (warp == mma_warp) tmem_alloc<TMEM_COLS>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -423,12 +431,15 @@ tc_conv1_u8_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
     for (int i = 0; i < my_tiles; ++i) {
       const int s = i % U8_A_STAGES;
       const bool more = i + 1 < my_tiles;
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && i < 12;
+      if (tr) p.trace[i * 8 + 0] = clock64();
       if (more) fetch((int)blockIdx.x + (i + 1) * (int)gridDim.x);
       // kernel row kh of this pixel's patch = elements [4 + 6*ow, +16) of staged row 2*dr + kh: slot 0 is the element before the
       // patch (zero weight), slots 1..15 the 5 x 3 taps
       const uint8_t* src = pix + (i & 1) * U8_PIX_BUF + (2 * dr) * (U8_PIX_LD * 2) + (4 + 6 * ow) * 2;
       mbar_wait(&a_empty[s], ((uint32_t)(i / U8_A_STAGES) & 1u) ^ 1u);
       uint8_t* st = a_smem + s * U8_A_STAGE;
+      if (tr) p.trace[i * 8 + 1] = clock64();
 #pragma unroll
       for (int kh = 0; kh < 5; ++kh) {
         const uint32_t* q = reinterpret_cast<const uint32_t*>(src + kh * (U8_PIX_LD * 2));
@@ -440,71 +451,72 @@ tc_conv1_u8_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_full[s]);
+      if (tr) p.trace[i * 8 + 2] = clock64();
       if (more) stage(pix + ((i + 1) & 1) * U8_PIX_BUF);    // that buffer's last readers (tile i-1) passed the barrier below an iteration ago
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-  } else if (warp < C1_MMA_WARP) {
+  } else if (warp < mma_warp) {
     // ===================== epilogue: TMEM -> bias + ReLU + (hi, lo) split -> swizzled staging -> TMA tensor stores =====================
-    // The staging is eight 8 KB sub-tiles [hi|lo][channel half][32-channel chunk] of 128 slots x 64 B in the 64-byte-swizzle
-    // layout (conflict-free STS.128 from a thread-per-slot warp).  A tile is shipped in two phases (chunk 0 of both halves, then
-    // chunk 1): the stores of one phase drain while the other phase is being computed, so the 64 KB staging acts as a double
-    // buffer -- the epilogue never waits for its own stores unless HBM is the limit.
-    const int q = warp & 3, hsel = (warp - 4) >> 2, r = q * 32 + lane;
+    // Warp (q, g) owns the tile's slots [32 q, 32 q + 32) and the 32-channel chunks g, g + groups, ... (groups = n_epi / 4: one
+    // chunk per tile with sixteen warps, two with eight).  A chunk goes through 4 KB of the warp's own staging (hi 2 KB, lo 2 KB,
+    // 64-byte rows, 64-byte swizzle: conflict-free STS.128 from a thread-per-slot warp) and is shipped by the warp's own lane 0, so
+    // the tile's tensor stores are issued by n_epi lanes in parallel and no barrier couples the warps.  Sixteen warps: one buffer,
+    // reused a whole tile later; eight warps: one buffer per chunk, the stores of one drain under the math of the other.
+    const int q = warp & 3, g = (warp - 4) >> 2, groups = n_epi >> 2, per_warp = 4 / groups;
     const float us = p.unscale * p.out_scale;
-    constexpr int SUB = 128 * 64;                    // bytes of one sub-tile
-    const int rsw = (r >> 1) & 3;
-    int phase = 0;                                   // phases issued so far by this CTA (two per tile)
+    const int rsw = (lane >> 1) & 3;
+    uint8_t* wbuf = out_smem + (warp - 4) * (U8_OUT_BYTES / n_epi);
+    int ph = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int as = i & 1;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       mbar_wait(&acc_full[as], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128 && i < 12;
+      if (tr) p.trace[i * 8 + 5] = clock64();
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc, ++phase) {
+      for (int cc = 0; cc < per_warp; ++cc, ++ph) {
+        const int c0 = (g + cc * groups) * 32;           // first channel of this chunk
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + hsel * 64 + cc * 32), v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + c0), v);
         tmem_ld_wait();
-        uint32_t hi[16], lo[16];
-        float amax = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float a = fmaxf(fmaf(__uint_as_float(v[j]), us, bias_s[hsel * 64 + cc * 32 + j]), 0.f);
-          const float bb = fmaxf(fmaf(__uint_as_float(v[j + 1]), us, bias_s[hsel * 64 + cc * 32 + j + 1]), 0.f);
-          amax = fmaxf(amax, fmaxf(a, bb));
-          split_f16x2(a, bb, hi[j >> 1], lo[j >> 1]);
-        }
-        if (p.range_flag != nullptr && !(amax < 65520.f)) atomicOr(p.range_flag, 1u);
-        if (phase >= 2) {                            // this phase's sub-tiles were last shipped two phases ago: that group must have been read
-          if (warp == 4) bulk_wait_read_1();         // (meaningful in lane 0, which committed the stores: at most the newest group may be pending)
-          asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_EPI_WARPS) : "memory");
-        }
-        uint8_t* my_hi = out_smem + ((0 * 2 + hsel) * 2 + cc) * SUB + r * 64;
-        uint8_t* my_lo = out_smem + ((1 * 2 + hsel) * 2 + cc) * SUB + r * 64;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int ch = (j ^ rsw) << 4;
-          *reinterpret_cast<uint4*>(my_hi + ch) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          *reinterpret_cast<uint4*>(my_lo + ch) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-        }
-        if (cc == 1) {                               // both chunks of this warp's TMEM columns have been read
+        if (cc == per_warp - 1) {                        // this warp's TMEM columns have been read: the accumulator may be overwritten
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
-        fence_proxy_async_smem();                    // generic-proxy writes -> visible to the TMA engine
-        asm volatile("bar.sync 2, %0;" ::"n"(32 * C1_EPI_WARPS) : "memory");
-        if (warp == 4 && lane == 0) {
-          const int slot0 = tile * 128;              // slots are in tile order: tile t covers slots [128 t, 128 t + 128)
+        uint32_t hi[16], lo[16];
+        float amax = 0.f;
 #pragma unroll
-          for (int hs = 0; hs < 2; ++hs) {
-            tma_store_2d(&tm_out_hi, out_smem + ((0 * 2 + hs) * 2 + cc) * SUB, hs * 64 + cc * 32, slot0);
-            tma_store_2d(&tm_out_lo, out_smem + ((1 * 2 + hs) * 2 + cc) * SUB, hs * 64 + cc * 32, slot0);
-          }
+        for (int j = 0; j < 32; j += 2) {
+          const float a = fmaxf(fmaf(__uint_as_float(v[j]), us, bias_s[c0 + j]), 0.f);
+          const float bb = fmaxf(fmaf(__uint_as_float(v[j + 1]), us, bias_s[c0 + j + 1]), 0.f);
+          amax = fmaxf(amax, fmaxf(a, bb));
+          split_f16x2(a, bb, hi[j >> 1], lo[j >> 1]);
+        }
+        if (p.range_flag != nullptr && !(amax < 65520.f)) atomicOr(p.range_flag, 1u);
+        if (ph >= per_warp) {                            // the buffer was shipped per_warp chunks ago: only newer groups may still be unread
+          if (lane == 0) { if (per_warp == 2) bulk_wait_read_1(); else bulk_wait_read_all(); }
+          __syncwarp();
+        }
+        uint8_t* sb = wbuf + cc * 4096;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = (j ^ rsw) << 4;
+          *reinterpret_cast<uint4*>(sb + lane * 64 + ch) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<uint4*>(sb + 2048 + lane * 64 + ch) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+        fence_proxy_async_smem();                        // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm_out_hi, sb, c0, tile * 128 + q * 32);
+          tma_store_2d(&tm_out_lo, sb + 2048, c0, tile * 128 + q * 32);
           bulk_commit_group();
         }
       }
+      if (tr) p.trace[i * 8 + 6] = clock64();
     }
-    if (warp == 4 && lane == 0) bulk_wait_all();     // all stores landed before the CTA exits
+    if (lane == 0) bulk_wait_all();                      // all stores landed before the CTA exits
   } else {
     // ===================== weight TMA + MMA issuer (last warp) =====================
     if (lane == 0) {
@@ -519,7 +531,9 @@ tc_conv1_u8_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
       for (int i = 0; i < my_tiles; ++i) {
         const int s = i % U8_A_STAGES, as = i & 1;
         mbar_wait(&acc_empty[as], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        if (p.trace != nullptr && blockIdx.x == 0 && i < 12) p.trace[i * 8 + 3] = clock64();
         mbar_wait(&a_full[s], (uint32_t)(i / U8_A_STAGES) & 1u);
+        if (p.trace != nullptr && blockIdx.x == 0 && i < 12) p.trace[i * 8 + 4] = clock64();
         tc_fence_after();
         const uint32_t ast = smem_u32(a_smem + s * U8_A_STAGE);
         const uint32_t d = tmem_base + (uint32_t)(as * N);
@@ -539,7 +553,7 @@ tc_conv1_u8_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == C1_MMA_WARP) {
+  if (warp == mma_warp) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
@@ -583,7 +597,7 @@ struct TcConv1 {
   CUtensorMap tm_hi, tm_lo;
   // uint8 kernel: weights with 1/255 folded in, 5 x 16 slot order; output tensor maps over conv2's (hi, lo) input
   __half *w8_hi = nullptr, *w8_lo = nullptr;
-  CUtensorMap tm8_hi, tm8_lo, tm_out_hi, tm_out_lo;
+  CUtensorMap tm8_hi, tm8_lo, tm_out32_hi, tm_out32_lo;   // output maps: one box = a warp's 32 slots x 32 channels
   const __half *bound_hi = nullptr, *bound_lo = nullptr;
   long long slots = 0;            // 256-byte output slots the tensor maps cover ((b, oh/2, ow/2, parity) positions)
   bool u8_ok = false;
@@ -645,6 +659,7 @@ int tc_conv1_pack(TcConv1* h, const float* w_dev, int K, float w_scale, unsigned
 int tc_conv1_forward(TcConv1* h, const aae_net_cfg* cfg, const void* crops, int src_u8, int B, const float* bias, float act_scale,
                      float w_scale, __half* out_hi, __half* out_lo, unsigned* range_flag, cudaStream_t s) {
   Conv1Params p;
+  p.trace = nullptr;
   p.range_flag = range_flag;
   p.x = crops; p.B = B; p.H = cfg->in_h; p.W = cfg->in_w; p.C = cfg->in_c;
   p.OH = cfg->in_h / 2; p.OW = cfg->in_w / 2; p.N = h->N;
@@ -667,13 +682,31 @@ int tc_conv1_forward(TcConv1* h, const aae_net_cfg* cfg, const void* crops, int 
     if (h->bound_hi != out_hi || h->bound_lo != out_lo || h->slots != slots) {
       const uint64_t dims[2] = {128, (uint64_t)slots};
       const uint64_t strides[1] = {256};
-      const uint32_t box[2] = {32, 128};                    // 32 channels x 128 slots = one 8 KB staging sub-tile, 64-byte swizzle
-      AAE_TRY(make_tmap_f16(&h->tm_out_hi, out_hi, 2, dims, strides, box, 64));
-      AAE_TRY(make_tmap_f16(&h->tm_out_lo, out_lo, 2, dims, strides, box, 64));
+      const uint32_t box32[2] = {32, 32};                   // one warp's 32 slots x 32 channels, 64-byte swizzle
+      AAE_TRY(make_tmap_f16(&h->tm_out32_hi, out_hi, 2, dims, strides, box32, 64));
+      AAE_TRY(make_tmap_f16(&h->tm_out32_lo, out_lo, 2, dims, strides, box32, 64));
       h->bound_hi = out_hi; h->bound_lo = out_lo; h->slots = slots;
     }
     p.unscale = 1.f / (w_scale * 256.f);              // accumulators hold sum u8 * (w * w_scale * 256 / 255)
-    tc_conv1_u8_kernel<<<grid, C1_THREADS, U8_SMEM_TOTAL, s>>>(h->tm8_hi, h->tm8_lo, h->tm_out_hi, h->tm_out_lo, p);
+    const char* epi8 = getenv("AAE_C1_EPI8");               // read per launch (scripts/ab_inproc.py): "1" = eight epilogue warps
+    const int u8_threads = 32 * (4 + ((epi8 && epi8[0] == '1') ? 8 : U8_MAX_EPI_WARPS) + 1);
+    static long long* trace_dev = nullptr;
+    p.trace = nullptr;
+    if (getenv("AAE_C1_TRACE")) {
+      if (!trace_dev) cudaMalloc(&trace_dev, 96 * sizeof(long long));
+      cudaMemsetAsync(trace_dev, 0, 96 * sizeof(long long), s);
+      p.trace = trace_dev;
+    }
+    tc_conv1_u8_kernel<<<grid, u8_threads, U8_SMEM_TOTAL, s>>>(h->tm8_hi, h->tm8_lo, h->tm_out32_hi, h->tm_out32_lo, p);
+    if (p.trace) {
+      long long t[96];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(t, p.trace, sizeof(t), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[conv1 trace, CTA 0, clocks from the first builder stamp] tile: builder start | stage free | built || issuer: accumulator free | operands ready || epilogue warp 4: start | end\n");
+      for (int i = 0; i < 12; ++i)
+        fprintf(stderr, "  tile %2d: %6lld | %6lld | %6lld || %6lld | %6lld || %6lld | %6lld\n", i, t[i * 8] - t[0], t[i * 8 + 1] - t[0], t[i * 8 + 2] - t[0],
+                t[i * 8 + 3] - t[0], t[i * 8 + 4] - t[0], t[i * 8 + 5] - t[0], t[i * 8 + 6] - t[0]);
+    }
   } else if (src_u8) {
     AAE_CUDA_OK(cudaFuncSetAttribute(tc_conv1_kernel<128, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     tc_conv1_kernel<128, 3, true><<<grid, C1_THREADS, S::TOTAL, s>>>(h->tm_hi, h->tm_lo, p);
