@@ -316,6 +316,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 
 struct TcTileSched {
   int m_pairs, n_tiles, splits;   // tiles = m_pairs * n_tiles * splits, each tile = 256 rows x 256 columns x one K range
+  int late_release;               // A/B: 1 = the epilogue warps release the accumulators only after their last chunk is shipped
   int tma_out;                    // > 0: tm_o_hi / tm_o_lo describe the output and each epilogue warp owns 4 KB of staging behind the ring:
                                   // 1 space-to-depth (hi, lo), 2 plain (hi, lo), 3 depth-to-space (hi, lo), 4 fp32 [M, N] (tm_o_hi only)
   long long* trace;               // AAE_TC_TRACE: clock64 of CTA 0 for its first 96 chunks: [g*4+0] TMA issued, +1 full barrier seen by the MMA thread, +2 MMAs issued, +3 stage seen empty again
@@ -443,6 +444,7 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       mbar_wait(tmem_full_bar, (uint32_t)tl & 1u);
       tc_fence_after();
       if (sch.trace && blockIdx.x == 0 && threadIdx.x == 128 && tl < 16) sch.trace[392 + tl * 4 + 2] = clock64();
+      bool released = false;
       if ((lean && sch.tma_out >= 1 && sch.tma_out <= 3) || sch.tma_out == 4) {
         // TMA-store epilogue: the warp parks its 32 pixels x 32 columns (hi and lo with 64-byte rows and 64-byte swizzle, or fp32
         // with 128-byte rows and 128-byte swizzle) in its own 4 KB of shared memory and one lane ships the box(es) with tensor
@@ -459,6 +461,12 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(N_TILE + c * 32), x);
           tmem_ld_wait();
+          if (c + epi_groups >= N_TILE / 32 && !sch.late_release) {   // last chunk of this warp: its accumulator words are in registers,
+            tc_fence_before();                                         // the issuer may overwrite TMEM while the warp finishes the chunk
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(empty_addr);
+            released = true;
+          }
           const int n = n0 + c * 32;
           if (mw >= p.M || n >= p.N) continue;
           if (sch.tma_out == 4) {
@@ -527,9 +535,11 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           tc_store_chunk(p, row, n, f, z);
         }
       }
-      tc_fence_before();                                        // this warp's TMEM reads are complete
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(empty_addr);
+      if (!released) {
+        tc_fence_before();                                      // this warp's TMEM reads are complete
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(empty_addr);
+      }
       if (sch.trace && blockIdx.x == 0 && threadIdx.x == 128 && tl < 16) sch.trace[392 + tl * 4 + 3] = clock64();
     }
     if (lane == 0) bulk_wait_all();                               // this warp's tensor stores have landed before the CTA exits
@@ -654,6 +664,8 @@ int launch_tc_gemm2(const TcLayer& L, dim3 grid, cudaStream_t s) {
     const bool tma_out = tma_out_on && L.tma_out && f32_target_ok && STAGES * S::STAGE_BYTES + 2048 + EPI_TMA * 4096 <= 232448;
     const int threads = tma_out ? 128 + 32 * EPI_TMA : tc_block_threads();
     const int smem_bytes = tma_out ? STAGES * S::STAGE_BYTES + 2048 + EPI_TMA * 4096 : S::TOTAL;
+    const char* late = getenv("AAE_TC_LATE_RELEASE");            // read per launch (scripts/ab_inproc.py)
+    sch.late_release = (late && late[0] == '1') ? 1 : 0;
     sch.tma_out = !tma_out ? 0 : L.gp.out_mode == OUT_S2D_SPLIT ? 1 : L.gp.out_mode == OUT_PLAIN_SPLIT ? 2 : L.gp.out_mode == OUT_D2S_SPLIT ? 3 : 4;
     AAE_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem_bytes, (int)S::TOTAL)));
     static int pair_slots = 0;                       // CTA pairs that can be resident at once (asked from the driver: pairs cannot straddle GPCs)
